@@ -1,0 +1,151 @@
+/*
+ * sslam_b200.h — C ABI of libsslam_b200.so, the B200 (sm_100a) replacement for the per-frame
+ * learned-feature front-end of Siverteh/semantic-slam-master.
+ *
+ * The reference is pure Python and has no FFI of its own; its boundary for this path is the
+ * method surface cited at each entry point below (paths relative to <reference>/semantic-slam/).
+ * A reference-side binding (ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch tensors) unless it says host;
+ *  - the library never allocates caller-visible memory, never synchronises the stream and never
+ *    throws across the ABI; work is enqueued on `stream` (a cudaStream_t) and the call returns;
+ *  - return value: SSLAM_OK (0) or a negative SSLAM_E* code; sslam_last_error() gives the text
+ *    (thread-local);
+ *  - there is no CPU fallback: on a machine without an sm_100 device every compute entry point
+ *    returns SSLAM_ENODEVICE.
+ *  - tie rules: top-k order is (score descending, linear index y*W+x ascending); argmax returns
+ *    the lowest maximal index (NumPy / torch-CPU behaviour).
+ */
+#ifndef SSLAM_B200_H_
+#define SSLAM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSLAM_ABI_VERSION 1
+
+enum {
+  SSLAM_OK = 0,
+  SSLAM_EINVAL = -1,       /* bad argument (null pointer, negative size, floor < 0 ...)        */
+  SSLAM_EUNSUPPORTED = -2, /* shape outside what the kernels implement (see each entry point)  */
+  SSLAM_EWORKSPACE = -3,   /* workspace smaller than sslam_*_workspace_bytes()                 */
+  SSLAM_ECUDA = -4,        /* a CUDA runtime call failed; text in sslam_last_error()           */
+  SSLAM_ENODEVICE = -5     /* no CUDA device of compute capability 10.x                        */
+};
+
+/* decode `info` columns, int32 [B,4] */
+enum {
+  SSLAM_INFO_BRANCH = 0,     /* 0 main (keypoint_selector.py:120-128), 1 lower percentile (:139-156),
+                                2 raw padding (:157-173), 3 raw top-k (:174-184),
+                                -1 the reference would raise: topk with k > H*W (:166,178)      */
+  SSLAM_INFO_NCAND = 1,      /* candidates above the main threshold; -1 when the fast path proved
+                                "at least K" without computing the exact count                  */
+  SSLAM_INFO_TIES = 2,       /* entries equal to the k-th score that were left out               */
+  SSLAM_INFO_NLOCALMAX = 3   /* NMS survivors above the lowest floor                             */
+};
+
+/* similarity arithmetic for sslam_match_top2 */
+enum {
+  SSLAM_SIM_F32 = 0,    /* fp32 FMA on CUDA cores (exact-mode reference implementation)          */
+  SSLAM_SIM_TF32X3 = 1, /* tcgen05 kind::tf32, 3-term hi/lo split, fp32 accumulate in TMEM       */
+  SSLAM_SIM_BF16 = 2    /* tcgen05 kind::f16 on bf16 copies, fp32 accumulate in TMEM             */
+};
+
+/* acceptance rule for sslam_match_finalize; params[] meaning per variant */
+enum {
+  SSLAM_MATCH_M1 = 1, /* visualize_matches.py:102-124      params[0] = ratio_thresh              */
+  SSLAM_MATCH_M2 = 2, /* visualize_matches_sequence.py:106-197  params = {saliency_weight,
+                         min_saliency, min_descriptor_sim, min_intensity, 1 - saliency_weight
+                         (rounded to fp32 by the caller, as Python computes it in double)}       */
+  SSLAM_MATCH_M3 = 3, /* test/test_descriptor_quality.py:97-142  params[0] = ratio_threshold     */
+  SSLAM_MATCH_M4 = 4, /* train.py:410-449                  mutual NN only                        */
+  SSLAM_MATCH_M5 = 5  /* test/test_tracking.py:159-161     params[0] = match_threshold, no mutual */
+};
+
+int sslam_abi_version(void);
+
+/* Copies the calling thread's last error text into buf (host); returns its length. */
+int sslam_last_error(char* buf, size_t len);
+
+/* 0 when the current CUDA device is compute capability 10.x, else SSLAM_ENODEVICE / SSLAM_ECUDA. */
+int sslam_device_check(void);
+
+/* Number of kernel launches (not memsets) this process enqueued through the library so far. */
+uint64_t sslam_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heatmap decode.  Replaces KeypointSelector.select_keypoints / _apply_nms and, with
+ * from_logits != 0, the sigmoid tail of KeypointSelector.forward
+ * (models/keypoint_selector.py:69-207, 209-226, 61-62).
+ *
+ *   sal      [B,H,W] fp32 saliency (or logits)        kpts_xy [B,K,2] fp32 (x,y), integer valued
+ *   scores   [B,K] fp32                               info    [B,4] int32 (SSLAM_INFO_*), may be NULL
+ *   pct      min_score_percentile (reference default 0.50);  floor: 0.1 in the reference (>= 0)
+ *   nms_radius 0..8
+ * Limits: 1 <= K <= 16384, H*W <= 2^24 (torch.quantile's own limit).
+ * All B maps are decoded by the same launches; there is no host synchronisation.
+ */
+size_t sslam_decode_workspace_bytes(int B, int H, int W, int K);
+int sslam_decode_topk_f32(const float* sal, int from_logits, int B, int H, int W, int K,
+                          int nms_radius, float pct, float floor, float* kpts_xy, float* scores,
+                          int32_t* info, void* ws, size_t ws_bytes, void* stream);
+
+/* NMS only (KeypointSelector._apply_nms, keypoint_selector.py:209-226): out = sal where sal equals
+ * its (2r+1)^2 neighbourhood maximum, else 0.  sal/out [B,H,W]. */
+int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radius, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bilinear descriptor sampling.  Replaces DinoBackbone.extract_at_keypoints
+ * (models/dino_backbone.py:114-152) with ATen-identical coordinate arithmetic and zero padding.
+ *   feat [B,h,w,C] fp32 NHWC      kpts [B,N,2] fp32 (x,y)      out [B,N,C] fp32
+ *   coords: 0 = keypoints are in patch units (drop-in);
+ *           1 = keypoints are in pixel units and DinoBackbone.pixel_to_patch (:167-178,
+ *               (p-8)/16) is applied first.
+ */
+int sslam_gather_bilinear_f32(const float* feat, const float* kpts, int B, int h, int w, int C,
+                              int N, int coords, float* out, void* stream);
+
+/* Row-wise L2 normalisation, the tail of DescriptorRefiner.forward
+ * (models/descriptor_refiner.py:86): out = in / max(||in||_2, eps).
+ *   in [rows,D] fp32;  out_f32 [rows,D] fp32 or NULL;  out_bf16 [rows,D] bf16 or NULL. */
+int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f32,
+                      void* out_bf16, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Matching primitive shared by M1..M5: over the virtual S_p = D1_p . D2_p^T (never stored)
+ *   per row    nn12 (lowest argmax), best12, second12 (second entry of the row sorted descending,
+ *              -inf when M == 1);     [P,N]
+ *   per column nn21 (lowest argmax), best21;   [P,M]
+ * Pair p reads rows  bank1 + a*N*D  and  bank2 + b*M*D  where (a,b) = pair_index[p] if
+ * pair_index != NULL (int32 [P,2], device) else (p,p).  `dtype` is SSLAM_SIM_*; banks are fp32 for
+ * SSLAM_SIM_F32 / SSLAM_SIM_TF32X3 and bf16 for SSLAM_SIM_BF16.  D % 4 == 0, D <= 256.
+ * Replaces visualize_matches.py:105-109,117-119; visualize_matches_sequence.py:144-146;
+ * test/test_descriptor_quality.py:116-130; train.py:422-424; test/test_tracking.py:159-160.
+ */
+size_t sslam_match_workspace_bytes(int P, int N, int M, int D, int dtype);
+int sslam_match_top2(const void* bank1, const void* bank2, const int32_t* pair_index, int dtype,
+                     int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
+                     int32_t* nn21, float* best21, void* ws, size_t ws_bytes, void* stream);
+
+/* Acceptance rules + ordered compaction (ascending i).
+ *   pairs [P,N,2] int32, rows beyond counts[p] are -1;  pair_scores [P,N] fp32;  counts [P] int32
+ *   pair_scores: M1/M4/M5 similarity, M2 quality, M3 1 - similarity.
+ *   scores1/scores2 (saliency per keypoint, banks [*,N] / [*,M]) are required for M2;
+ *   inten1/inten2 optional (M2).  They are indexed by the same (a,b) as the descriptor banks.
+ */
+int sslam_match_finalize(int variant, const float* params /* host, 8 floats */,
+                         const int32_t* pair_index, int P, int N, int M, const int32_t* nn12,
+                         const float* best12, const float* second12, const int32_t* nn21,
+                         const float* best21, const float* scores1, const float* scores2,
+                         const float* inten1, const float* inten2, int32_t* pairs,
+                         float* pair_scores, int32_t* counts, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSLAM_B200_H_ */

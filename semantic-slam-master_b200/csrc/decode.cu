@@ -1,0 +1,495 @@
+// Heatmap decode for B maps at once, no host synchronisation.
+//
+// Replaces KeypointSelector.select_keypoints/_apply_nms (models/keypoint_selector.py:69-226).
+//
+// Data flow (per call, all images in every launch):
+//   K1 scan     : one DRAM read of the map, smem-tiled (2r+1)^2 NMS, local maxima appended to a
+//                 per-image candidate list as 64-bit keys (score bits << 32 | ~linear index)
+//   K2 topk     : per image, exact K-th largest key (adaptive radix select), compaction, bitonic
+//                 sort in smem -> tentative main-branch output (score desc, index asc)
+//   K3 count    : second pass over the map (L2 resident): how many pixels are < the K-th score
+//   K4 resolve  : the main branch (keypoint_selector.py:120-128) is taken iff at least K NMS
+//                 survivors exceed thr = max(quantile(map, p), floor).  Because the quantile lies
+//                 between order statistics v[lo] <= thr32 <= v[hi], "count(pixels < kth score) >
+//                 hi" proves thr32 < kth score without computing the quantile.  When the proof
+//                 fails (few maxima, tiny grids, constant maps) this kernel computes the exact
+//                 quantile(s) and reproduces the reference's fallback branches (:130-184).
+//
+// The common case therefore never sorts or histograms the full map; the exact-quantile machinery
+// only runs for images that really need the reference's fallback arithmetic.
+#include "common.cuh"
+
+namespace sslam {
+namespace {
+
+constexpr int TILE_W = 128;
+constexpr int TILE_H = 32;
+constexpr int MAX_R = 8;
+constexpr int SCAN_THREADS = 256;
+constexpr int SEL_THREADS = 1024;
+constexpr float LOWER_FLOOR = 0.05f;     // keypoint_selector.py:141
+
+struct __align__(16) ImgHeader {
+  u32 cand_count;      // local maxima appended by K1
+  u32 below_count;     // pixels strictly below the K-th candidate score (K3)
+  u64 kth_key;         // K-th largest candidate key (K2); 0 when fewer than K candidates
+  u32 have_tentative;  // K2 wrote a tentative main-branch result
+  u32 ties;            // candidates equal to the K-th score left unselected
+  u32 pad[2];
+};
+
+struct DecodeParams {
+  const float* sal;
+  int from_logits;
+  int B, H, W, K, r;
+  float pct, floor;
+  float* kpts;
+  float* scores;
+  int32_t* info;
+  ImgHeader* hdr;
+  u64* cand;           // [B][H*W]
+};
+
+__device__ __forceinline__ float load_px(const DecodeParams& p, size_t off) {
+  float v = __ldg(p.sal + off);
+  return p.from_logits ? sigmoid_f32(v) : v;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+__global__ void __launch_bounds__(SCAN_THREADS) decode_scan_kernel(DecodeParams p) {
+  extern __shared__ float smem[];
+  const int r = p.r, H = p.H, W = p.W;
+  const int inW = TILE_W + 2 * r, inH = TILE_H + 2 * r;
+  float* tin = smem;                 // [inH][inW]
+  float* hmx = smem + inH * inW;     // [inH][TILE_W]
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const size_t img = (size_t)b * H * W;
+  const float NEG_INF = __int_as_float(0xff800000);
+
+  for (int i = threadIdx.x; i < inH * inW; i += SCAN_THREADS) {
+    int ty = i / inW, tx = i - ty * inW;
+    int y = y0 + ty - r, x = x0 + tx - r;
+    float v = NEG_INF;                                    // max_pool2d pads with -inf (:215-220)
+    if (y >= 0 && y < H && x >= 0 && x < W) v = load_px(p, img + (size_t)y * W + x);
+    tin[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < inH * TILE_W; i += SCAN_THREADS) {
+    int ty = i / TILE_W, tx = i - ty * TILE_W;
+    const float* row = tin + ty * inW + tx;
+    float m = row[0];
+    for (int d = 1; d <= 2 * r; ++d) m = fmaxf(m, row[d]);
+    hmx[i] = m;
+  }
+  __syncthreads();
+  const float min_keep = fminf(p.floor, LOWER_FLOOR);     // nothing at or below can ever pass
+  ImgHeader* hdr = p.hdr + b;
+  u64* cand = p.cand + (size_t)b * H * W;
+  for (int i = threadIdx.x; i < TILE_H * TILE_W; i += SCAN_THREADS) {
+    int ty = i / TILE_W, tx = i - ty * TILE_W;
+    int y = y0 + ty, x = x0 + tx;
+    bool is_max = false;
+    float c = 0.f;
+    if (y < H && x < W) {
+      const float* col = hmx + ty * TILE_W + tx;
+      float m = col[0];
+      for (int d = 1; d <= 2 * r; ++d) m = fmaxf(m, col[d * TILE_W]);
+      c = tin[(ty + r) * inW + tx + r];
+      is_max = (c == m) && (c > min_keep);                // plateaus survive (:223)
+    }
+    unsigned bal = __ballot_sync(0xffffffffu, is_max);
+    if (bal) {
+      int lane = threadIdx.x & 31;
+      int leader = __ffs(bal) - 1;
+      u32 base = 0;
+      if (lane == leader) base = atomicAdd(&hdr->cand_count, (u32)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (is_max) {
+        u32 pos = base + __popc(bal & ((1u << lane) - 1));
+        u32 lin = (u32)(y * W + x);
+        cand[pos] = ((u64)__float_as_uint(c) << 32) | (u64)(0xffffffffu - lin);   // c > 0
+      }
+    }
+  }
+}
+
+// Plain NMS output (drop-in for _apply_nms)
+__global__ void __launch_bounds__(SCAN_THREADS) nms_kernel(const float* sal, int H, int W, int r,
+                                                           float* out) {
+  extern __shared__ float smem[];
+  const int inW = TILE_W + 2 * r, inH = TILE_H + 2 * r;
+  float* tin = smem;
+  float* hmx = smem + inH * inW;
+  const int b = blockIdx.z;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * TILE_H;
+  const size_t img = (size_t)b * H * W;
+  const float NEG_INF = __int_as_float(0xff800000);
+  for (int i = threadIdx.x; i < inH * inW; i += SCAN_THREADS) {
+    int ty = i / inW, tx = i - ty * inW;
+    int y = y0 + ty - r, x = x0 + tx - r;
+    float v = NEG_INF;
+    if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(sal + img + (size_t)y * W + x);
+    tin[i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < inH * TILE_W; i += SCAN_THREADS) {
+    int ty = i / TILE_W, tx = i - ty * TILE_W;
+    const float* row = tin + ty * inW + tx;
+    float m = row[0];
+    for (int d = 1; d <= 2 * r; ++d) m = fmaxf(m, row[d]);
+    hmx[i] = m;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TILE_H * TILE_W; i += SCAN_THREADS) {
+    int ty = i / TILE_W, tx = i - ty * TILE_W;
+    int y = y0 + ty, x = x0 + tx;
+    if (y < H && x < W) {
+      const float* col = hmx + ty * TILE_W + tx;
+      float m = col[0];
+      for (int d = 1; d <= 2 * r; ++d) m = fmaxf(m, col[d * TILE_W]);
+      float c = tin[(ty + r) * inW + tx + r];
+      out[img + (size_t)y * W + x] = __fmul_rn(c, (c == m) ? 1.0f : 0.0f);          // :223-224
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K2
+struct CandSrc {
+  const u64* keys;
+  __device__ __forceinline__ bool operator()(int i, u64& k) const { k = keys[i]; return true; }
+};
+
+// Select the `count` largest keys of a filtered stream, sort them descending in `buf`
+// (capacity pow2 >= count) and return through `buf`.  Returns the count-th largest key.
+template <typename Src>
+__device__ u64 block_topk_sorted(Src src, int n, int count, u64* buf, int cap_pow2,
+                                 SelectScratch* ss, u32* counter) {
+  u64 kth = block_select_kth_largest(src, n, (u32)count, ss);
+  if (threadIdx.x == 0) *counter = 0;
+  for (int i = threadIdx.x; i < cap_pow2; i += blockDim.x) buf[i] = 0;
+  __syncthreads();
+  // keys strictly above kth first, then as many == kth as needed (keys may repeat in raw mode)
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    u64 k;
+    if (src(i, k) && k > kth) buf[atomicAdd(counter, 1u)] = k;
+  }
+  __syncthreads();
+  u32 above = *counter;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    u64 k;
+    if (src(i, k) && k == kth) {
+      u32 pos = atomicAdd(counter, 1u);
+      if (pos < (u32)count) buf[pos] = k;
+    }
+  }
+  (void)above;
+  __syncthreads();
+  block_bitonic_sort_desc(buf, cap_pow2);
+  return kth;
+}
+
+__device__ __forceinline__ void write_row(const DecodeParams& p, int b, int row, u32 lin, float sc) {
+  size_t o = (size_t)b * p.K + row;
+  p.kpts[2 * o] = (float)(lin % (u32)p.W);       // x = column  (:127)
+  p.kpts[2 * o + 1] = (float)(lin / (u32)p.W);   // y = row
+  p.scores[o] = sc;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) decode_topk_kernel(DecodeParams p, int kpad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* buf = reinterpret_cast<u64*>(smem_raw);                        // [kpad]
+  SelectScratch* ss = reinterpret_cast<SelectScratch*>(buf + kpad);
+  __shared__ u32 counter;
+  __shared__ u32 eq_total;
+  const int b = blockIdx.x;
+  ImgHeader* hdr = p.hdr + b;
+  const int n = (int)hdr->cand_count;
+  if (n < p.K) {                       // cannot be the main branch; K4 takes the exact path
+    if (threadIdx.x == 0) { hdr->kth_key = 0; hdr->have_tentative = 0; hdr->ties = 0; }
+    return;
+  }
+  CandSrc src{p.cand + (size_t)b * p.H * p.W};
+  if (threadIdx.x == 0) eq_total = 0;
+  u64 kth = block_topk_sorted(src, n, p.K, buf, kpad, ss, &counter);
+  for (int i = threadIdx.x; i < p.K; i += blockDim.x) {
+    u64 k = buf[i];
+    write_row(p, b, i, key_index(k), __uint_as_float((u32)(k >> 32)));
+  }
+  // ties at the k-th boundary: same score, not selected
+  u32 ksc = (u32)(kth >> 32);
+  u32 local = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    u64 k = src.keys[i];
+    if ((u32)(k >> 32) == ksc && k < kth) ++local;
+  }
+  local = warp_reduce_sum(local);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&eq_total, local);
+  __syncthreads();
+  if (threadIdx.x == 0) { hdr->kth_key = kth; hdr->have_tentative = 1; hdr->ties = eq_total; }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+__global__ void __launch_bounds__(256) decode_count_kernel(DecodeParams p, int chunks_per_img) {
+  __shared__ u32 red[33];
+  const int b = blockIdx.x / chunks_per_img;
+  const int chunk = blockIdx.x - b * chunks_per_img;
+  ImgHeader* hdr = p.hdr + b;
+  if (!hdr->have_tentative) return;
+  const float kth = __uint_as_float((u32)(hdr->kth_key >> 32));
+  const int n = p.H * p.W;
+  const size_t img = (size_t)b * n;
+  const int per = (n + chunks_per_img - 1) / chunks_per_img;
+  const int beg = chunk * per, end = min(n, beg + per);
+  u32 c = 0;
+  for (int i = beg + threadIdx.x; i < end; i += 256) c += (load_px(p, img + i) < kth) ? 1u : 0u;
+  c = block_reduce_sum(c, red);
+  if (threadIdx.x == 0 && c) atomicAdd(&hdr->below_count, c);
+}
+
+// ------------------------------------------------------------------------------------------ K4
+struct PixelValSrc {                    // all pixels, key = ordered value (for quantiles)
+  DecodeParams p; size_t img;
+  __device__ __forceinline__ bool operator()(int i, u64& k) const {
+    k = (u64)ordered_from_float(load_px(p, img + i));
+    return true;
+  }
+};
+struct PixelKeySrc {                    // all pixels, key = (value, ~index)  (raw topk, :166,178)
+  DecodeParams p; size_t img;
+  __device__ __forceinline__ bool operator()(int i, u64& k) const {
+    k = pack_key(load_px(p, img + i), (u32)i);
+    return true;
+  }
+};
+struct CandBandSrc {                    // candidates with lo < score <= hi  (hi = +inf: score > lo)
+  const u64* keys; float lo, hi;
+  __device__ __forceinline__ bool operator()(int i, u64& k) const {
+    k = keys[i];
+    float s = __uint_as_float((u32)(k >> 32));
+    return (s > lo) && !(s > hi);
+  }
+};
+
+// torch.quantile(flat, q) (keypoint_selector.py:106,140), then max(., floor) as fp32
+__device__ float block_exact_threshold(const DecodeParams& p, size_t img, float q, float floor,
+                                       SelectScratch* ss) {
+  const int n = p.H * p.W;
+  float rank = __fmul_rn(q, (float)(n - 1));
+  int lo = (int)floorf(rank), hi = (int)ceilf(rank);
+  float w = __fsub_rn(rank, (float)lo);
+  PixelValSrc src{p, img};
+  // ascending index lo == (n - lo)-th largest
+  float vlo = float_from_ordered((u32)block_select_kth_largest(src, n, (u32)(n - lo), ss));
+  float vhi = vlo;
+  if (hi != lo) vhi = float_from_ordered((u32)block_select_kth_largest(src, n, (u32)(n - hi), ss));
+  return fmaxf(lerp_aten(vlo, vhi, w), floor);
+}
+
+__device__ u32 block_count_band(const u64* keys, int n, float lo, float hi, u32* red) {
+  CandBandSrc s{keys, lo, hi};
+  u32 c = 0;
+  u64 k;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) c += s(i, k) ? 1u : 0u;
+  return block_reduce_sum(c, red);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) decode_resolve_kernel(DecodeParams p, int kpad) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* buf = reinterpret_cast<u64*>(smem_raw);
+  SelectScratch* ss = reinterpret_cast<SelectScratch*>(buf + kpad);
+  __shared__ u32 counter;
+  __shared__ u32 red[33];
+  const int b = blockIdx.x;
+  ImgHeader* hdr = p.hdr + b;
+  const int npx = p.H * p.W;
+  const size_t img = (size_t)b * npx;
+  const int ncand = (int)hdr->cand_count;
+  const u64* cand = p.cand + (size_t)b * npx;
+  const float INF = __int_as_float(0x7f800000);
+  int32_t* info = p.info ? p.info + 4 * b : nullptr;
+
+  // ---- fast proof of the main branch
+  {
+    float rank = __fmul_rn(p.pct, (float)(npx - 1));
+    int hi = (int)ceilf(rank);
+    float kth = __uint_as_float((u32)(hdr->kth_key >> 32));
+    if (hdr->have_tentative && hdr->below_count > (u32)hi && kth > p.floor) {
+      if (info && threadIdx.x == 0) {
+        info[0] = 0; info[1] = -1; info[2] = (int32_t)hdr->ties; info[3] = ncand;
+      }
+      return;
+    }
+  }
+  // ---- exact path (keypoint_selector.py:105-117)
+  const float thr = block_exact_threshold(p, img, p.pct, p.floor, ss);
+  const int n = (int)block_count_band(cand, ncand, thr, INF, red);
+  if (n >= p.K) {                                            // main branch after all (:120-128)
+    if (info && threadIdx.x == 0) {
+      info[0] = 0; info[1] = n; info[2] = (int32_t)hdr->ties; info[3] = ncand;
+    }
+    return;                                                  // K2's result stands
+  }
+  int branch, ties = 0, row0 = 0, remaining = p.K;
+  if (n > 0) {                                               // :130-137
+    // first group: the n candidates in row-major order -> sort by ascending linear index
+    if (threadIdx.x == 0) counter = 0;
+    for (int i = threadIdx.x; i < kpad; i += blockDim.x) buf[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+      u64 k = cand[i];
+      if (__uint_as_float((u32)(k >> 32)) > thr)
+        buf[atomicAdd(&counter, 1u)] = ((k & 0xffffffffull) << 32) | (k >> 32);   // (~lin, score)
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(buf, kpad);                      // ~lin descending == lin ascending
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      u64 k = buf[i];
+      write_row(p, b, i, 0xffffffffu - (u32)(k >> 32), __uint_as_float((u32)k));
+    }
+    __syncthreads();
+    row0 = n;
+    remaining = p.K - n;                                     // :136
+    branch = -2;
+    const float pcts[4] = {0.40f, 0.30f, 0.20f, 0.10f};      // :139
+    for (int t = 0; t < 4; ++t) {
+      float lthr = block_exact_threshold(p, img, pcts[t], LOWER_FLOOR, ss);   // :140-141
+      // additional = nms > lthr and not valid (:143)
+      int m = (int)block_count_band(cand, ncand, lthr, thr, red);
+      if (m >= remaining) {                                  // :147-156
+        CandBandSrc src{cand, lthr, thr};
+        u64 kth = block_topk_sorted(src, ncand, remaining, buf, kpad, ss, &counter);
+        for (int i = threadIdx.x; i < remaining; i += blockDim.x) {
+          u64 k = buf[i];
+          write_row(p, b, row0 + i, key_index(k), __uint_as_float((u32)(k >> 32)));
+        }
+        u32 ksc = (u32)(kth >> 32), local = 0;
+        u64 k;
+        for (int i = threadIdx.x; i < ncand; i += blockDim.x)
+          if (src(i, k) && (u32)(k >> 32) == ksc && k < kth) ++local;
+        ties = (int)block_reduce_sum(local, red);
+        branch = 1;
+        break;
+      }
+    }
+    if (branch == -2) branch = 2;                            // for/else (:157-173)
+  } else {
+    branch = 3;                                              // :174-184
+  }
+  if (branch == 2 || branch == 3) {
+    if (remaining > npx) {                                   // topk raises (:166,178)
+      if (info && threadIdx.x == 0) { info[0] = -1; info[1] = n; info[2] = 0; info[3] = ncand; }
+      return;
+    }
+    PixelKeySrc src{p, img};
+    u64 kth = block_topk_sorted(src, npx, remaining, buf, kpad, ss, &counter);
+    for (int i = threadIdx.x; i < remaining; i += blockDim.x) {
+      u64 k = buf[i];
+      write_row(p, b, row0 + i, key_index(k), key_value(k));
+    }
+    u32 ksc = (u32)(kth >> 32), local = 0;
+    u64 k;
+    for (int i = threadIdx.x; i < npx; i += blockDim.x)
+      if (src(i, k) && (u32)(k >> 32) == ksc && k < kth) ++local;
+    ties = (int)block_reduce_sum(local, red);
+  }
+  // keypoint_selector.py:186-199 (trim / duplicate padding) is unreachable: every branch above
+  // produced exactly K rows.
+  if (info && threadIdx.x == 0) { info[0] = branch; info[1] = n; info[2] = ties; info[3] = ncand; }
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+size_t hdr_bytes(int B) { return align_up((size_t)B * sizeof(ImgHeader), 256); }
+
+}  // namespace
+}  // namespace sslam
+
+using namespace sslam;
+
+extern "C" size_t sslam_decode_workspace_bytes(int B, int H, int W, int K) {
+  (void)K;
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return hdr_bytes(B) + (size_t)B * H * W * sizeof(u64);
+}
+
+extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, int H, int W, int K,
+                                     int nms_radius, float pct, float floor, float* kpts_xy,
+                                     float* scores, int32_t* info, void* ws, size_t ws_bytes,
+                                     void* stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SSLAM_REQUIRE(B >= 0 && H > 0 && W > 0 && K >= 0, SSLAM_EINVAL, "decode: negative size");
+  if (B == 0 || K == 0) return SSLAM_OK;
+  SSLAM_REQUIRE(sal && kpts_xy && scores && ws, SSLAM_EINVAL, "decode: null pointer");
+  SSLAM_REQUIRE(floor >= 0.f, SSLAM_EINVAL, "decode: floor must be >= 0");
+  SSLAM_REQUIRE(pct >= 0.f && pct <= 1.f, SSLAM_EINVAL,
+                "decode: quantile() q values must be in the range [0, 1]");
+  SSLAM_REQUIRE(nms_radius >= 0 && nms_radius <= MAX_R, SSLAM_EUNSUPPORTED,
+                "decode: nms_radius %d outside 0..%d", nms_radius, MAX_R);
+  SSLAM_REQUIRE(K <= 16384, SSLAM_EUNSUPPORTED, "decode: K=%d > 16384", K);
+  SSLAM_REQUIRE((long long)H * W <= (1ll << 24), SSLAM_EUNSUPPORTED,
+                "decode: quantile() input tensor is too large (H*W > 2^24)");
+  SSLAM_REQUIRE(ws_bytes >= sslam_decode_workspace_bytes(B, H, W, K), SSLAM_EWORKSPACE,
+                "decode: workspace %zu < %zu", ws_bytes, sslam_decode_workspace_bytes(B, H, W, K));
+
+  DecodeParams p;
+  p.sal = sal; p.from_logits = from_logits; p.B = B; p.H = H; p.W = W; p.K = K; p.r = nms_radius;
+  p.pct = pct; p.floor = floor; p.kpts = kpts_xy; p.scores = scores; p.info = info;
+  p.hdr = reinterpret_cast<ImgHeader*>(ws);
+  p.cand = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws) + hdr_bytes(B));
+  SSLAM_CHECK_CUDA(cudaMemsetAsync(p.hdr, 0, (size_t)B * sizeof(ImgHeader), stream));
+
+  const int r = nms_radius;
+  size_t scan_smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
+  dim3 g1((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
+  decode_scan_kernel<<<g1, SCAN_THREADS, scan_smem, stream>>>(p);
+  SSLAM_LAUNCHED();
+
+  const int kpad = next_pow2(K);
+  size_t sel_smem = (size_t)kpad * 8 + sizeof(SelectScratch);
+  static std::atomic<size_t> configured{0};
+  if (configured.load() < sel_smem) {
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_topk_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_resolve_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured.store(160 * 1024);
+  }
+  decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad);
+  SSLAM_LAUNCHED();
+
+  int chunks = (H * W + 16383) / 16384;
+  if (chunks < 1) chunks = 1;
+  decode_count_kernel<<<B * chunks, 256, 0, stream>>>(p, chunks);
+  SSLAM_LAUNCHED();
+
+  decode_resolve_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}
+
+extern "C" int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radius, float* out,
+                             void* stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SSLAM_REQUIRE(B >= 0 && H > 0 && W > 0, SSLAM_EINVAL, "nms: negative size");
+  if (B == 0) return SSLAM_OK;
+  SSLAM_REQUIRE(sal && out, SSLAM_EINVAL, "nms: null pointer");
+  SSLAM_REQUIRE(nms_radius >= 0 && nms_radius <= MAX_R, SSLAM_EUNSUPPORTED,
+                "nms: nms_radius %d outside 0..%d", nms_radius, MAX_R);
+  if (nms_radius == 0) {                                     // identity (:211-212)
+    SSLAM_CHECK_CUDA(cudaMemcpyAsync(out, sal, (size_t)B * H * W * 4, cudaMemcpyDeviceToDevice,
+                                     stream));
+    return SSLAM_OK;
+  }
+  const int r = nms_radius;
+  size_t smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
+  dim3 g((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
+  nms_kernel<<<g, SCAN_THREADS, smem, stream>>>(sal, H, W, r, out);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}

@@ -1,0 +1,181 @@
+"""Tensor-in / tensor-out wrappers over the C ABI.  All tensors live on the current CUDA device;
+work is enqueued on torch's current stream; nothing here synchronises."""
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+SIM_F32, SIM_TF32X3, SIM_BF16 = 0, 1, 2
+M1, M2, M3, M4, M5 = 1, 2, 3, 4, 5
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sslam_b200 operates on CUDA tensors only (no CPU fallback)")
+
+
+def launch_count():
+    return int(_lib.load().sslam_launch_count())
+
+
+class Workspace:
+    """Grow-only device scratch buffer (one per stream of use)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self.buf
+
+
+_default_ws = {}
+
+
+def _ws(kind, nbytes, device):
+    key = (kind, device.index, torch.cuda.current_stream().cuda_stream)
+    w = _default_ws.setdefault(key, Workspace())
+    return w.get(nbytes, device)
+
+
+def decode_topk(saliency, num_keypoints, nms_radius=2, min_score_percentile=0.5, floor=0.1,
+                from_logits=False, out=None, workspace=None):
+    """Fused decode of B maps: saliency (B,H,W) or (B,H,W,1) fp32 ->
+    keypoints (B,K,2) fp32 (x,y), scores (B,K) fp32, info (B,4) int32."""
+    lib = _lib.load()
+    _need_cuda(saliency)
+    sal = saliency[..., 0] if saliency.dim() == 4 else saliency
+    if sal.dtype != torch.float32:
+        raise RuntimeError("decode_topk expects fp32 saliency")
+    sal = sal.contiguous()
+    B, H, W = sal.shape
+    K = int(num_keypoints)
+    if out is None:
+        kp = torch.empty(B, K, 2, dtype=torch.float32, device=sal.device)
+        sc = torch.empty(B, K, dtype=torch.float32, device=sal.device)
+        info = torch.empty(B, 4, dtype=torch.int32, device=sal.device)
+    else:
+        kp, sc, info = out
+    need = lib.sslam_decode_workspace_bytes(B, H, W, K)
+    ws = workspace if workspace is not None else _ws("decode", need, sal.device)
+    _lib.check(lib.sslam_decode_topk_f32(_ptr(sal), int(bool(from_logits)), B, H, W, K,
+                                         int(nms_radius), float(min_score_percentile), float(floor),
+                                         _ptr(kp), _ptr(sc), _ptr(info), _ptr(ws), ws.numel(),
+                                         _stream()))
+    return kp, sc, info
+
+
+def nms(saliency, radius):
+    """saliency (B,H,W) fp32 -> same shape, non-maxima zeroed."""
+    lib = _lib.load()
+    _need_cuda(saliency)
+    sal = saliency.contiguous()
+    B, H, W = sal.shape
+    out = torch.empty_like(sal)
+    _lib.check(lib.sslam_nms_f32(_ptr(sal), B, H, W, int(radius), _ptr(out), _stream()))
+    return out
+
+
+def gather_bilinear(features, keypoints, pixel_coords=False, out=None):
+    """features (B,h,w,C) fp32 NHWC, keypoints (B,N,2) fp32 -> (B,N,C) fp32."""
+    lib = _lib.load()
+    _need_cuda(features, keypoints)
+    feat = features.contiguous()
+    kp = keypoints.contiguous()
+    if feat.dtype != torch.float32 or kp.dtype != torch.float32:
+        raise RuntimeError("gather_bilinear expects fp32 tensors")
+    B, h, w, C = feat.shape
+    N = kp.shape[1]
+    if out is None:
+        out = torch.empty(B, N, C, dtype=torch.float32, device=feat.device)
+    _lib.check(lib.sslam_gather_bilinear_f32(_ptr(feat), _ptr(kp), B, h, w, C, N,
+                                             1 if pixel_coords else 0, _ptr(out), _stream()))
+    return out
+
+
+def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False):
+    """x (..., D) fp32 -> x / max(||x||, eps); optionally also a bf16 copy."""
+    lib = _lib.load()
+    _need_cuda(x)
+    xc = x.contiguous()
+    D = xc.shape[-1]
+    rows = xc.numel() // D
+    if out is None:
+        out = torch.empty_like(xc)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device)
+    _lib.check(lib.sslam_l2norm_rows(_ptr(xc), rows, D, float(eps), _ptr(out), _ptr(out_bf16),
+                                     _stream()))
+    return (out, out_bf16) if want_bf16 else out
+
+
+def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, workspace=None):
+    """Row top-2 / column argmax of S_p = D1_p . D2_p^T without storing S.
+
+    bank1 (F1,N,D), bank2 (F2,M,D); pair_index (P,2) int32 selects (a,b) per pair, default (p,p).
+    Returns dict(nn12, best12, second12 (P,N); nn21, best21 (P,M))."""
+    lib = _lib.load()
+    _need_cuda(bank1, bank2, pair_index)
+    if not (bank1.is_contiguous() and bank2.is_contiguous()):
+        raise RuntimeError("descriptor banks must be contiguous")
+    want = torch.bfloat16 if mode == SIM_BF16 else torch.float32
+    if bank1.dtype != want or bank2.dtype != want:
+        raise RuntimeError(f"mode {mode} expects {want} descriptor banks")
+    N, D = bank1.shape[-2], bank1.shape[-1]
+    M = bank2.shape[-2]
+    if pair_index is not None:
+        pair_index = pair_index.to(torch.int32).contiguous()
+        P = pair_index.shape[0]
+    else:
+        P = int(num_pairs) if num_pairs is not None else min(bank1.shape[0], bank2.shape[0])
+    dev = bank1.device
+    res = dict(nn12=torch.empty(P, N, dtype=torch.int32, device=dev),
+               best12=torch.empty(P, N, dtype=torch.float32, device=dev),
+               second12=torch.empty(P, N, dtype=torch.float32, device=dev),
+               nn21=torch.empty(P, M, dtype=torch.int32, device=dev),
+               best21=torch.empty(P, M, dtype=torch.float32, device=dev))
+    need = lib.sslam_match_workspace_bytes(P, N, M, D, mode)
+    ws = workspace if workspace is not None else _ws("match", need, dev)
+    _lib.check(lib.sslam_match_top2(_ptr(bank1), _ptr(bank2), _ptr(pair_index), int(mode), P, N, M,
+                                    D, _ptr(res["nn12"]), _ptr(res["best12"]), _ptr(res["second12"]),
+                                    _ptr(res["nn21"]), _ptr(res["best21"]), _ptr(ws), ws.numel(),
+                                    _stream()))
+    return res
+
+
+def match_finalize(variant, top, params, pair_index=None, scores1=None, scores2=None,
+                   inten1=None, inten2=None):
+    """Apply acceptance rule `variant` to the output of match_top2.
+    Returns pairs (P,N,2) int32 (-1 padded), pair_scores (P,N) fp32, counts (P,) int32."""
+    lib = _lib.load()
+    nn12 = top["nn12"]
+    P, N = nn12.shape
+    M = top["nn21"].shape[1]
+    dev = nn12.device
+    if pair_index is not None:
+        pair_index = pair_index.to(torch.int32).contiguous()
+    pairs = torch.empty(P, N, 2, dtype=torch.int32, device=dev)
+    pscores = torch.empty(P, N, dtype=torch.float32, device=dev)
+    counts = torch.empty(P, dtype=torch.int32, device=dev)
+    prm = (ctypes.c_float * 8)(*([float(v) for v in params] + [0.0] * (8 - len(params))))
+    for t in (scores1, scores2, inten1, inten2):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+            raise RuntimeError("score / intensity banks must be contiguous fp32")
+    _lib.check(lib.sslam_match_finalize(int(variant), prm, _ptr(pair_index), P, N, M, _ptr(nn12),
+                                        _ptr(top["best12"]), _ptr(top["second12"]), _ptr(top["nn21"]),
+                                        _ptr(top["best21"]), _ptr(scores1), _ptr(scores2),
+                                        _ptr(inten1), _ptr(inten2), _ptr(pairs), _ptr(pscores),
+                                        _ptr(counts), _stream()))
+    return pairs, pscores, counts

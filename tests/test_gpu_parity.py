@@ -1,0 +1,342 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures written by the
+reference's own functions, and against the oracle run live on identical seeded inputs.
+
+Bar: bit-exact for keypoint coordinates, scores, indices and match pairs (top-k tie order and
+similarity near-ties < 1e-6 excepted and counted); floating-point outputs within the tolerance
+written next to each assertion.
+"""
+
+import json
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import recipes
+from parity import compare_keypoints, compare_matches, load_golden
+from test_oracle_golden import (DEC, DEC_CASES, DEC_META, MAT, MAT_META, decode_case_input,
+                                match_case_input)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from sslam_b200 import _lib
+    assert _lib.load().sslam_device_check() == 0, _lib.last_error()
+    return torch.device("cuda", 0)
+
+
+def cu(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+# ------------------------------------------------------------------------------------ decode
+@pytest.mark.parametrize("name", DEC_CASES)
+def test_decode_golden(name, dev):
+    from sslam_b200 import ops
+    sal, m = decode_case_input(name)
+    kp, sc, info = ops.decode_topk(cu(sal[None], dev), m["K"], m["nms_radius"], m["pct"])
+    kp, sc, info = kp.cpu().numpy()[0], sc.cpu().numpy()[0], info.cpu().numpy()[0]
+    _, _, oinfo = oracle.select_keypoints(sal[None], m["K"], m["nms_radius"], m["pct"])
+    assert info[0] == oinfo[0, 0], "branch differs from oracle"
+    if info[1] >= 0:
+        assert info[1] == oinfo[0, 1]
+    assert info[2] == oinfo[0, 2], "tie count differs from oracle"
+    n = int(oinfo[0, 1])
+    compare_keypoints(sal, DEC[name + ".kpts"], DEC[name + ".scores"], kp, sc,
+                      sorted_from=n if info[0] in (1, 2) else 0)
+    # our own tie rule is deterministic: identical to the oracle, position by position
+    okp, osc, _ = oracle.select_keypoints(sal[None], m["K"], m["nms_radius"], m["pct"])
+    assert np.array_equal(okp[0], kp) and np.array_equal(osc[0], sc)
+
+
+def test_decode_mixed_batch(dev):
+    """Several maps of one size in a single call take different branches independently."""
+    from sslam_b200 import ops
+    maps = [recipes.spread_saliency(48, 64, 101), np.full((48, 64), 0.05, np.float32),
+            recipes.box_saliency(48, 64, 102, quant=16), recipes.spread_saliency(48, 64, 103)]
+    three = np.full((48, 64), 0.2, np.float32)
+    three[5, 5], three[20, 30], three[40, 60] = 0.9, 0.8, 0.7
+    maps.append(three)
+    batch = np.stack(maps)
+    for K in (16, 64, 600):
+        kp, sc, info = ops.decode_topk(cu(batch, dev), K)
+        okp, osc, oinfo = oracle.select_keypoints(batch, K)
+        assert np.array_equal(info.cpu().numpy()[:, 0], oinfo[:, 0])
+        assert np.array_equal(kp.cpu().numpy(), okp)
+        assert np.array_equal(sc.cpu().numpy(), osc)
+    assert len(set(oinfo[:, 0].tolist())) >= 2
+
+
+def test_decode_native_grid_c0(dev):
+    from models.keypoint_selector import KeypointSelector
+    sel = KeypointSelector(384, 256).to(dev)
+    kp, sc = sel.select_keypoints(cu(DEC["c0.sal"], dev)[..., None], num_keypoints=500)
+    assert kp.shape == (2, 500, 2) and kp.dtype == torch.float32
+    assert np.array_equal(kp.cpu().numpy(), DEC["c0.kpts"])
+    assert np.array_equal(sc.cpu().numpy(), DEC["c0.scores"])
+
+
+def test_decode_raises_like_reference(dev):
+    from models.keypoint_selector import KeypointSelector
+    sel = KeypointSelector(384, 256).to(dev)
+    sal = cu(recipes.spread_saliency(30, 40, 5)[None, :, :, None], dev)
+    with pytest.raises(RuntimeError, match="selected index k out of range"):
+        sel.select_keypoints(sal, num_keypoints=2048)
+
+
+def test_decode_from_logits(dev):
+    from sslam_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    logits = (torch.randn(2, 64, 96, generator=g) * 2).to(dev)
+    kp, sc, _ = ops.decode_topk(logits, 50, from_logits=True)
+    sal = torch.sigmoid(logits)
+    # every score is the sigmoid of the logit at its keypoint (<= 2 ulp: device expf vs torch)
+    xs, ys = kp[..., 0].long(), kp[..., 1].long()
+    picked = torch.stack([sal[b, ys[b], xs[b]] for b in range(2)])
+    assert torch.allclose(picked, sc, rtol=3e-7, atol=0)
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all())
+
+
+def test_nms_golden(dev):
+    from models.keypoint_selector import KeypointSelector
+    sel = KeypointSelector(8, 8)
+    x = cu(DEC["nms.in"][None], dev)
+    for r in range(4):
+        out = sel._apply_nms(x, r)
+        assert np.array_equal(out.cpu().numpy()[0], DEC[f"nms.r{r}"])
+
+
+def test_decode_full_size_properties(dev):
+    """BASELINE sizes (640x480 K=2048, 1280x960 K=8192) on the seeded synthetic sequence:
+    identical to the oracle, plus size-independent properties."""
+    from sslam_b200 import ops, synth
+    for (H, W, K, T) in ((480, 640, 2048, 3), (960, 1280, 8192, 1)):
+        sal, _ = synth.make_sequence(T, seq_id=0, height=H, width=W)
+        kp, sc, info = ops.decode_topk(sal.to(dev), K)
+        kp, sc, info = kp.cpu().numpy(), sc.cpu().numpy(), info.cpu().numpy()
+        okp, osc, oinfo = oracle.select_keypoints(sal.numpy(), K)
+        assert np.array_equal(info[:, 0], oinfo[:, 0]) and (info[:, 0] == 0).all()
+        assert np.array_equal(kp, okp) and np.array_equal(sc, osc)
+        s = sal.numpy()[..., 0]
+        for b in range(T):
+            assert (np.diff(sc[b]) <= 0).all()                          # sorted
+            lin = kp[b, :, 1].astype(np.int64) * W + kp[b, :, 0].astype(np.int64)
+            assert np.unique(lin).size == K                              # no duplicates
+            assert np.array_equal(s[b].ravel()[lin], sc[b])              # scores are map values
+            assert (sc[b] > max(np.median(s[b]), 0.1)).all()             # above the threshold
+            nms = oracle.apply_nms(s[b], 2).ravel()
+            assert (nms[lin] > 0).all()                                  # all are NMS survivors
+
+
+# ------------------------------------------------------------------------------------ gather / norm
+def test_gather_golden(dev):
+    from models.dino_backbone import DinoBackbone
+    z, _ = load_golden("gather")
+    bb = DinoBackbone(load_vit=False).to(dev)
+    out = bb.extract_at_keypoints(cu(z["small.feat"], dev), cu(z["small.kpts"], dev)).cpu().numpy()
+    assert np.abs(out - z["small.out"]).max() <= 1e-6
+    assert np.array_equal(out, z["small.out"]), "gather is expected to be bit-identical to ATen CPU"
+    feat = recipes.int_features(1, 30, 40, 384, 43)
+    pc = bb.pixel_to_patch(cu(z["tum.pix"], dev))
+    assert np.array_equal(pc.cpu().numpy(), z["tum.patch"])
+    assert np.array_equal(bb.patch_to_pixel(pc).cpu().numpy(), z["tum.back"])
+    out = bb.extract_at_keypoints(cu(feat, dev), pc).cpu().numpy()
+    assert np.array_equal(out, z["tum.out"])
+    fused = bb.extract_at_pixel_keypoints(cu(feat, dev), cu(z["tum.pix"], dev)).cpu().numpy()
+    assert np.array_equal(fused, z["tum.out"]), "fused pixel_to_patch differs"
+    out = bb.extract_at_keypoints(cu(z["native.feat"], dev), cu(z["native.kpts"], dev)).cpu().numpy()
+    assert np.array_equal(out, z["native.out"])
+
+
+def test_gather_unaligned_channels(dev):
+    from sslam_b200 import ops
+    feat = recipes.int_features(2, 5, 6, 10, 7)          # C % 4 != 0 -> scalar path
+    rng = np.random.Generator(np.random.PCG64(8))
+    kp = np.stack([rng.integers(-32, 6 * 32 + 32, size=(2, 33)) / 32.0,
+                   rng.integers(-32, 5 * 32 + 32, size=(2, 33)) / 32.0], -1).astype(np.float32)
+    out = ops.gather_bilinear(cu(feat, dev), cu(kp, dev)).cpu().numpy()
+    assert np.array_equal(out, oracle.extract_at_keypoints(feat, kp))
+
+
+def test_refiner_and_normalize_golden(dev):
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import ops
+    z, _ = load_golden("refiner")
+    m = DescriptorRefiner(input_dim=48, hidden_dim=64, output_dim=32, num_layers=4)
+    m.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")})
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(cu(z["x"], dev)).cpu().numpy()
+    assert out.shape == z["out"].shape
+    assert np.abs(out - z["out"]).max() < 1e-5                          # descriptors within 1e-5 abs
+    nrm, nrm16 = ops.l2norm_rows(cu(z["norm.in"], dev), want_bf16=True)
+    assert np.allclose(nrm.cpu().numpy(), z["norm.out"], rtol=1e-6, atol=1e-7)
+    assert bool((nrm[3] == 0).all())
+    assert torch.allclose(nrm16.float(), nrm, rtol=8e-3, atol=1e-6)     # bf16 rounding
+    odd = cu(recipes.int_features(1, 1, 5, 10, 9).reshape(5, 10), dev)  # D % 4 != 0
+    assert np.allclose(ops.l2norm_rows(odd).cpu().numpy(), oracle.l2_normalize(odd.cpu().numpy()),
+                       rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------ matching
+def _top_cpu(top, p=0):
+    return {k: v[p].cpu().numpy() for k, v in top.items()}
+
+
+@pytest.mark.parametrize("name", list(MAT_META))
+def test_matchers_golden(name, dev):
+    from sslam_b200 import matchers
+    d1, d2, m = match_case_input(name)
+    if d1.shape[1] % 4:
+        pytest.skip("D % 4 != 0")
+    S = (d1.astype(np.float64) @ d2.astype(np.float64).T)
+    s1, s2, i1, i2 = (MAT[f"{name}.{k}"] for k in ("s1", "s2", "i1", "i2"))
+    exc = 0
+
+    got = matchers.find_matches(d1, d2, 0.8)
+    assert all(isinstance(t, tuple) and len(t) == 3 for t in got)
+    gp = np.array([(i, j) for i, j, _ in got], dtype=np.int64).reshape(-1, 2)
+    assert (np.diff(gp[:, 0]) > 0).all()                                  # ascending i
+    exc += compare_matches(S, MAT[name + ".m1"], gp)
+    if gp.shape == MAT[name + ".m1"].shape and np.array_equal(gp, MAT[name + ".m1"]):
+        assert np.allclose([s for _, _, s in got], MAT[name + ".m1s"], rtol=1e-6, atol=1e-6)
+    second = lambda i: np.partition(S[i], -2)[-2] if S.shape[1] > 1 else -1.0  # noqa: E731
+    got = matchers.find_matches(d1, d2, 1.02)
+    exc += compare_matches(S, MAT[name + ".m1b"], np.array([(i, j) for i, j, _ in got]).reshape(-1, 2),
+                           threshold_margin=lambda i, j: abs(S[i, j] - 1.02 * max(second(i), -1.0)))
+
+    mm, qq = matchers.match_with_quality(d1, d2, s1, s2)
+    assert mm.dtype == np.int64 and qq.dtype == np.float32 and mm.ndim == 2 and mm.shape[1] == 2
+    exc += compare_matches(S, MAT[name + ".m2"], mm, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
+    if np.array_equal(mm, MAT[name + ".m2"]):
+        assert np.allclose(qq, MAT[name + ".m2q"], rtol=1e-6, atol=1e-6)
+    mi, _ = matchers.match_with_quality(d1, d2, s1, s2, intensity1=i1, intensity2=i2,
+                                        min_intensity=0.15, min_saliency=0.5)
+    exc += compare_matches(S, MAT[name + ".m2i"], mi, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
+    me, qe = matchers.match_with_quality(d1, d2, s1, s2, min_descriptor_sim=1.5)
+    assert me.shape == (0, 2) and me.dtype == np.int64 and qe.shape == (0,) and qe.dtype == np.float32
+
+    if m["m"] >= 2:
+        m3, dist = matchers.find_mutual_nearest_neighbors(d1, d2, 0.9)
+        ratio_margin = lambda thr: (lambda i, j: abs(second(i) / (S[i, j] + 1e-8) - thr))  # noqa: E731
+        exc += compare_matches(S, MAT[name + ".m3"], m3, threshold_margin=ratio_margin(0.9))
+        if np.array_equal(m3, MAT[name + ".m3"]):
+            assert np.allclose(dist, MAT[name + ".m3d"], rtol=1e-5, atol=1e-6)
+        m3b, _ = matchers.find_mutual_nearest_neighbors(d1, d2, 0.98)
+        exc += compare_matches(S, MAT[name + ".m3b"], m3b, threshold_margin=ratio_margin(0.98))
+    if m["n"] == m["m"]:
+        b1 = cu(np.stack([d1, d2[::-1].copy()]), dev)
+        b2 = cu(np.stack([d2, d1]), dev)
+        o4 = matchers.find_matches_batched(b1, b2).cpu().numpy()
+        ref4 = MAT[name + ".m4"]
+        assert o4.dtype == np.int64
+        if o4.shape == ref4.shape and np.array_equal(o4, ref4):
+            pass
+        else:
+            for b in range(2):
+                Sb = (np.stack([d1, d2[::-1]])[b].astype(np.float64) @ np.stack([d2, d1])[b].astype(np.float64).T)
+                strip = lambda a: a[(a != 0).any(axis=1) | (np.arange(a.shape[0]) == 0)]  # noqa: E731
+                exc += compare_matches(Sb, strip(ref4[b]), strip(o4[b]))
+    assert matchers.tracking_count(d1, d2, 0.8) == int(MAT[name + ".m5"])
+    assert matchers.tracking_count(d1, d2, 0.5) == int(MAT[name + ".m5lo"])
+    print(f"{name}: near-tie exceptions {exc}")
+
+
+def test_match_top2_primitive_vs_oracle(dev):
+    """Row top-2 / column argmax incl. ragged sizes, exact ties and pair indexing."""
+    from sslam_b200 import ops
+    cases = [(130, 257, 32), (128, 128, 256), (1, 5, 16), (300, 1, 64), (77, 129, 100)]
+    for (n, m, d) in cases:
+        d1, d2, _ = recipes.descriptor_pair(n, m, d, 200 + n, noise=2, dup_every=9)
+        top = ops.match_top2(cu(d1[None], dev), cu(d2[None], dev))
+        t = _top_cpu(top)
+        nn12, best12, second12, nn21, best21, S = oracle.similarity_top2(d1, d2)
+        S64 = d1.astype(np.float64) @ d2.astype(np.float64).T
+        # values within fp32 accumulation error; indices equal unless a near tie
+        assert np.allclose(t["best12"], best12, rtol=0, atol=2e-6)
+        assert np.allclose(t["best21"], best21, rtol=0, atol=2e-6)
+        if m > 1:
+            assert np.allclose(t["second12"], second12, rtol=0, atol=2e-6)
+        else:
+            assert np.isneginf(t["second12"]).all()
+        for i in np.nonzero(t["nn12"] != nn12)[0]:
+            assert abs(S64[i, t["nn12"][i]] - S64[i, nn12[i]]) < 1e-6
+        for j in np.nonzero(t["nn21"] != nn21)[0]:
+            assert abs(S64[t["nn21"][j], j] - S64[nn21[j], j]) < 1e-6
+    # exact duplicates: lowest index must win in both directions
+    d1 = np.zeros((6, 8), np.float32); d1[:, 0] = 1
+    d2 = np.zeros((5, 8), np.float32); d2[:, 0] = 1
+    t = _top_cpu(ops.match_top2(cu(d1[None], dev), cu(d2[None], dev)))
+    assert (t["nn12"] == 0).all() and (t["nn21"] == 0).all()
+    assert (t["best12"] == 1).all() and (t["second12"] == 1).all()
+    # pair_index into banks
+    bank1 = np.stack([recipes.descriptor_pair(64, 64, 32, s)[0] for s in range(4)])
+    bank2 = np.stack([recipes.descriptor_pair(64, 80, 32, s)[1] for s in range(3)])
+    idx = torch.tensor([[3, 0], [1, 2], [0, 0]], dtype=torch.int32, device=dev)
+    top = ops.match_top2(cu(bank1, dev), cu(bank2, dev), pair_index=idx)
+    for p, (a, b) in enumerate(idx.cpu().tolist()):
+        nn12, best12, *_ = oracle.similarity_top2(bank1[a], bank2[b])
+        assert np.array_equal(top["nn12"][p].cpu().numpy(), nn12)
+        assert np.allclose(top["best12"][p].cpu().numpy(), best12, atol=2e-6)
+
+
+# ------------------------------------------------------------------------------------ end to end
+def test_sequence_pipeline_vs_oracle(dev):
+    """c2-shaped slice: 4 frames 640x480, K=2048, D=256, fp32 mode; keypoints identical, descriptors
+    within 1e-5 abs, consecutive-pair M1 and M2 lists identical up to counted near ties."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    T, K = 4, 2048
+    sal, feat = synth.make_sequence(T, seq_id=0)
+    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel")
+    feats, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1, chunk=3)
+    kp = feats["keypoints_pixel"].cpu().numpy()
+    okp, osc, oinfo = oracle.select_keypoints(sal.numpy(), K)
+    assert np.array_equal(kp, okp) and np.array_equal(feats["scores"].cpu().numpy(), osc)
+    g = oracle.extract_at_keypoints(feat.numpy(), oracle.pixel_to_patch(okp))
+    w = oracle.RefinerWeights.from_state_dict(refiner.state_dict())
+    od = oracle.refiner_forward(w, g)
+    d = feats["descriptors"].cpu().numpy()
+    assert np.abs(od - d).max() < 1e-5
+    assert np.allclose(np.linalg.norm(d, axis=-1), 1.0, atol=1e-5)
+    p2, q2, c2 = fe.match_consecutive(feats, matchers.M2)
+    total_exc = 0
+    for p in range(T - 1):
+        S = d[p].astype(np.float64) @ d[p + 1].astype(np.float64).T
+        ref = oracle.match_m1(d[p], d[p + 1], 0.8)
+        got = pairs[p, :int(counts[p])].cpu().numpy()
+        assert (pairs[p, int(counts[p]):] == -1).all()
+        total_exc += compare_matches(S, np.array([(i, j) for i, j, _ in ref]).reshape(-1, 2), got)
+        rm, rq = oracle.match_m2(d[p], d[p + 1], osc[p], osc[p + 1])
+        gm = p2[p, :int(c2[p])].cpu().numpy()
+        total_exc += compare_matches(S, rm, gm, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
+        if np.array_equal(rm, gm):
+            assert np.allclose(q2[p, :int(c2[p])].cpu().numpy(), rq, rtol=1e-5, atol=1e-6)
+        assert int(counts[p]) > K // 4, "overlapping frames should match plentifully"
+    print("sequence near-tie exceptions:", total_exc)
+
+
+def test_abi_error_codes(dev):
+    import ctypes
+    from sslam_b200 import _lib
+    l = _lib.load()
+    z = ctypes.c_void_p(0)
+    buf = torch.empty(1 << 20, dtype=torch.uint8, device=dev)
+    p = ctypes.c_void_p(buf.data_ptr())
+    assert l.sslam_decode_topk_f32(z, 0, 1, 8, 8, 4, 2, 0.5, 0.1, z, z, z, z, 0, z) == -1       # null
+    assert l.sslam_decode_topk_f32(p, 0, 1, 8, 8, 4, 99, 0.5, 0.1, p, p, p, p, 1 << 20, z) == -2  # radius
+    assert l.sslam_decode_topk_f32(p, 0, 1, 8, 8, 4, 2, 0.5, 0.1, p, p, p, p, 8, z) == -3        # workspace
+    assert l.sslam_decode_topk_f32(p, 0, 1, 8, 8, 4, 2, 0.5, -1.0, p, p, p, p, 1 << 20, z) == -1  # floor
+    assert "floor" in _lib.last_error()
+    assert l.sslam_decode_topk_f32(p, 0, 0, 8, 8, 4, 2, 0.5, 0.1, p, p, p, p, 0, z) == 0         # empty batch
+    assert l.sslam_match_top2(p, p, z, 0, 1, 4, 4, 6, p, p, p, p, p, p, 1 << 20, z) == -2        # D % 4
+    assert l.sslam_match_top2(p, p, z, 7, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1        # dtype
+    assert l.sslam_launch_count() > 0
+    torch.cuda.synchronize()
