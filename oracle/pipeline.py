@@ -1,0 +1,87 @@
+"""Oracle: the whole extract+match path on the CPU (test infrastructure / CPU baseline).
+
+Composition "pipeline P" of SURVEY.md §8(d): select_keypoints on the pixel-resolution saliency map
+-> pixel_to_patch -> extract_at_keypoints -> DescriptorRefiner (+ F.normalize) per frame, then a
+matcher per consecutive pair — the order of ``MatchVisualizer.extract_features`` /
+``SequenceMatcher.extract`` and ``process_spacing`` (visualize_matches.py:70-100,
+visualize_matches_sequence.py:69-104, 297-320), each frame extracted once.
+
+``run_sequence`` can fan frames / pairs out over a process pool so the CPU baseline uses every
+host core (the reference itself is single-process Python with intra-op BLAS threads).
+"""
+
+import os
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+from . import decode, gather, match, refiner
+
+_W = {}
+
+
+def extract_frame(sal, feat, weights, K, nms_radius=2, pct=0.5):
+    """sal (H,W) fp32, feat (h,w,C) fp32 -> keypoints_pixel (K,2), scores (K,), descriptors (K,D)."""
+    kp, sc, _ = decode.select_keypoints(sal[None], K, nms_radius, pct)
+    g = gather.extract_at_keypoints(feat[None], gather.pixel_to_patch(kp))
+    d = refiner.refiner_forward(weights, g)
+    return kp[0], sc[0], d[0]
+
+
+def match_pair(variant, d1, d2, s1, s2, **kw):
+    if variant == 1:
+        return match.match_m1(d1, d2, kw.get("ratio_thresh", 0.8))
+    if variant == 2:
+        return match.match_m2(d1, d2, s1, s2, **kw)
+    if variant == 3:
+        return match.match_m3(d1, d2, kw.get("ratio_threshold", 0.9))
+    raise ValueError(variant)
+
+
+def _init_worker(params, blas_threads):
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(blas_threads)
+    except Exception:
+        pass
+    _W["weights"] = refiner.RefinerWeights(params)
+
+
+def _extract_job(args):
+    sal, feat, K = args
+    return extract_frame(sal, feat, _W["weights"], K)
+
+
+def _match_job(args):
+    variant, d1, d2, s1, s2 = args
+    r = match_pair(variant, d1, d2, s1, s2)
+    return len(r) if isinstance(r, list) else r[0].shape[0]
+
+
+def run_sequence(sal, feat, weights, K, variant=1, workers=1):
+    """sal (T,H,W) fp32, feat (T,h,w,C) fp32 -> (per-pair match counts, seconds).
+    workers > 1 distributes frames, then pairs, over that many processes (1 BLAS thread each)."""
+    T = sal.shape[0]
+    t0 = time.perf_counter()
+    if workers <= 1:
+        ex = [extract_frame(sal[t], feat[t], weights, K) for t in range(T)]
+        counts = []
+        for t in range(T - 1):
+            r = match_pair(variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1])
+            counts.append(len(r) if isinstance(r, list) else r[0].shape[0])
+    else:
+        with ProcessPoolExecutor(workers, initializer=_init_worker,
+                                 initargs=(weights.p, 1)) as pool:
+            t0 = time.perf_counter()                      # pool start-up is not the algorithm
+            ex = list(pool.map(_extract_job, [(sal[t], feat[t], K) for t in range(T)]))
+            counts = list(pool.map(_match_job, [(variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1])
+                                                for t in range(T - 1)]))
+    return counts, time.perf_counter() - t0
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1

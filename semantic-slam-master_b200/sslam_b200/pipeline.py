@@ -26,13 +26,24 @@ class FrontEnd:
         self.K, self.r, self.pct = int(num_keypoints), int(nms_radius), float(min_score_percentile)
         self.grid, self.sim_mode, self.patch = grid, sim_mode, patch_size
 
+    def _mark(self, timers, name):
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timers.append((name, ev))
+
     @torch.no_grad()
-    def extract(self, saliency, features, out=None):
+    def extract(self, saliency, features, timers=None):
         """saliency (B,H,W,1)|(B,H,W), features (B,h,w,C) -> dict of device tensors:
-        keypoints_pixel (B,K,2), scores (B,K), descriptors (B,K,D) [, descriptors_bf16], info."""
+        keypoints_pixel (B,K,2), scores (B,K), descriptors (B,K,D) [, descriptors_bf16], info.
+        `timers`, when a list, receives (stage, cuda event) marks on the current stream."""
+        self._mark(timers, "begin")
         kp, sc, info = ops.decode_topk(saliency, self.K, self.r, self.pct)
+        self._mark(timers, "decode")
         sampled = ops.gather_bilinear(features, kp, pixel_coords=(self.grid == "pixel"))
+        self._mark(timers, "gather")
         raw = self.refiner.forward_unnormalized(sampled)
+        self._mark(timers, "refiner_mlp")
         B = kp.shape[0]
         res = dict(scores=sc, info=info)
         if self.sim_mode == SIM_BF16:
@@ -40,6 +51,7 @@ class FrontEnd:
             res["descriptors_bf16"] = d16.reshape(B, self.K, -1)
         else:
             d32 = ops.l2norm_rows(raw)
+        self._mark(timers, "l2norm")
         res["descriptors"] = d32.reshape(B, self.K, -1)
         res["keypoints_pixel"] = kp if self.grid == "pixel" else kp * self.patch + self.patch / 2
         return res
@@ -48,13 +60,18 @@ class FrontEnd:
         return feats["descriptors_bf16"] if self.sim_mode == SIM_BF16 else feats["descriptors"]
 
     @torch.no_grad()
-    def match_consecutive(self, feats, variant=matchers.M1, **kw):
+    def match_consecutive(self, feats, variant=matchers.M1, timers=None, **kw):
         """Match frame t with frame t+1 for every t of an extracted batch (P = B-1 pairs)."""
         bank = self.bank(feats)
         F = bank.shape[0]
         sc = feats["scores"]
-        return matchers.match(bank, bank[1:], variant, num_pairs=F - 1, mode=self.sim_mode,
-                              scores1=sc, scores2=sc[1:], **kw)[:3]
+        self._mark(timers, "begin")
+        top = ops.match_top2(bank, bank[1:], mode=self.sim_mode, num_pairs=F - 1)
+        self._mark(timers, "match_top2")
+        out = matchers.match(bank, bank[1:], variant, num_pairs=F - 1, mode=self.sim_mode,
+                             scores1=sc, scores2=sc[1:], top=top, **kw)[:3]
+        self._mark(timers, "match_finalize")
+        return out
 
     @torch.no_grad()
     def match_pairs(self, feats, pair_index, variant=matchers.M1, **kw):
@@ -65,13 +82,59 @@ class FrontEnd:
                               scores1=sc, scores2=sc, **kw)[:3]
 
     @torch.no_grad()
-    def run_sequence(self, saliency, features, variant=matchers.M1, chunk=64, **kw):
+    def run_sequence(self, saliency, features, variant=matchers.M1, chunk=64, timers=None, **kw):
         """Extract every frame once (in chunks) and match consecutive pairs.  Returns padded pair
         lists for the T-1 pairs, all on device."""
         T = saliency.shape[0]
         descs, descs16, scores, kps = [], [], [], []
         for s in range(0, T, chunk):
-            f = self.extract(saliency[s:s + chunk], features[s:s + chunk])
+            f = self.extract(saliency[s:s + chunk], features[s:s + chunk], timers=timers)
+            descs.append(f["descriptors"]); scores.append(f["scores"]); kps.append(f["keypoints_pixel"])
+            if self.sim_mode == SIM_BF16:
+                descs16.append(f["descriptors_bf16"])
+        feats = dict(descriptors=torch.cat(descs), scores=torch.cat(scores),
+                     keypoints_pixel=torch.cat(kps))
+        if descs16:
+            feats["descriptors_bf16"] = torch.cat(descs16)
+        pairs, pscores, counts = self.match_consecutive(feats, variant, timers=timers, **kw)
+        return feats, pairs, pscores, counts
+
+    @torch.no_grad()
+    def run_sequence_host(self, saliency_host, features_host, variant=matchers.M1, chunk=64,
+                          out_host=None, **kw):
+        """End-to-end entry point for HOST data: pinned (T,H,W,1) saliency and (T,h,w,C) features
+        are streamed to the device chunk by chunk on a copy stream (double-buffered, overlapping the
+        kernels of the previous chunk), every frame is extracted once, consecutive pairs are matched,
+        and the match lists are copied back.  Returns host tensors (pairs, pair_scores, counts)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        T = saliency_host.shape[0]
+        compute = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = {}
+        copy = self._copy_stream
+        key = (tuple(saliency_host.shape[1:]), tuple(features_host.shape[1:]), chunk)
+        if self._stage.get("key") != key:
+            self._stage = dict(key=key,
+                               sal=[torch.empty((chunk,) + tuple(saliency_host.shape[1:]), device=dev) for _ in range(2)],
+                               feat=[torch.empty((chunk,) + tuple(features_host.shape[1:]), device=dev) for _ in range(2)],
+                               free=[torch.cuda.Event(), torch.cuda.Event()])
+        st = self._stage
+        descs, descs16, scores, kps = [], [], [], []
+        copy.wait_stream(compute)
+        for ci, s in enumerate(range(0, T, chunk)):
+            e = min(T, s + chunk)
+            b = ci & 1
+            with torch.cuda.stream(copy):
+                if ci >= 2:
+                    copy.wait_event(st["free"][b])                   # previous user of this buffer done
+                st["sal"][b][:e - s].copy_(saliency_host[s:e], non_blocking=True)
+                st["feat"][b][:e - s].copy_(features_host[s:e], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            compute.wait_event(ready)
+            f = self.extract(st["sal"][b][:e - s], st["feat"][b][:e - s])
+            st["free"][b].record(compute)
             descs.append(f["descriptors"]); scores.append(f["scores"]); kps.append(f["keypoints_pixel"])
             if self.sim_mode == SIM_BF16:
                 descs16.append(f["descriptors_bf16"])
@@ -80,4 +143,11 @@ class FrontEnd:
         if descs16:
             feats["descriptors_bf16"] = torch.cat(descs16)
         pairs, pscores, counts = self.match_consecutive(feats, variant, **kw)
-        return feats, pairs, pscores, counts
+        if out_host is None:
+            out_host = (torch.empty(pairs.shape, dtype=pairs.dtype, pin_memory=True),
+                        torch.empty(pscores.shape, dtype=pscores.dtype, pin_memory=True),
+                        torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True))
+        for dst, src in zip(out_host, (pairs, pscores, counts)):
+            dst.copy_(src, non_blocking=True)
+        compute.synchronize()
+        return out_host
