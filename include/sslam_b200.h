@@ -121,14 +121,16 @@ int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f3
  *   per row    nn12 (lowest argmax), best12, second12 (second entry of the row sorted descending,
  *              -inf when M == 1);     [P,N]
  *   per column nn21 (lowest argmax), best21;   [P,M]
- * Pair p reads rows  bank1 + a*N*D  and  bank2 + b*M*D  where (a,b) = pair_index[p] if
- * pair_index != NULL (int32 [P,2], device) else (p,p).  `dtype` is SSLAM_SIM_*; banks are fp32 for
+ * bank1 holds F1 descriptor sets [F1,N,D], bank2 holds F2 sets [F2,M,D] (the banks may alias, e.g.
+ * bank2 = bank1 + N*D for consecutive-frame matching).  Pair p reads set a of bank1 and set b of
+ * bank2 where (a,b) = pair_index[p] if pair_index != NULL (int32 [P,2], device) else (p,p).  `dtype` is SSLAM_SIM_*; banks are fp32 for
  * SSLAM_SIM_F32 / SSLAM_SIM_TF32X3 and bf16 for SSLAM_SIM_BF16.  D % 4 == 0, D <= 256.
  * Replaces visualize_matches.py:105-109,117-119; visualize_matches_sequence.py:144-146;
  * test/test_descriptor_quality.py:116-130; train.py:422-424; test/test_tracking.py:159-160.
  */
-size_t sslam_match_workspace_bytes(int P, int N, int M, int D, int dtype);
-int sslam_match_top2(const void* bank1, const void* bank2, const int32_t* pair_index, int dtype,
+size_t sslam_match_workspace_bytes(int F1, int F2, int P, int N, int M, int D, int dtype);
+int sslam_match_top2(const void* bank1, int F1, const void* bank2, int F2,
+                     const int32_t* pair_index, int dtype,
                      int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                      int32_t* nn21, float* best21, void* ws, size_t ws_bytes, void* stream);
 

@@ -297,23 +297,24 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams f) {
 }  // namespace
 
 // implemented in match_tc.cu
-int match_top2_tc(const void* bank1, const void* bank2, const int32_t* pair_index, int dtype, int P,
-                  int N, int M, int D, int32_t* nn12, float* best12, float* second12, u64* colkeys,
-                  void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream);
-size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype);
+int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
+                  int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
+                  u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream);
+size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype, int F1, int F2);
 
 }  // namespace sslam
 
 using namespace sslam;
 
-extern "C" size_t sslam_match_workspace_bytes(int P, int N, int M, int D, int dtype) {
+extern "C" size_t sslam_match_workspace_bytes(int F1, int F2, int P, int N, int M, int D, int dtype) {
   if (P <= 0 || N <= 0 || M <= 0) return 0;
   size_t base = align_up((size_t)P * M * sizeof(u64), 256);
-  if (dtype != SSLAM_SIM_F32) base += match_tc_extra_workspace(P, N, M, D, dtype);
+  if (dtype != SSLAM_SIM_F32) base += match_tc_extra_workspace(P, N, M, D, dtype, F1, F2);
   return base;
 }
 
-extern "C" int sslam_match_top2(const void* bank1, const void* bank2, const int32_t* pair_index,
+extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, int F2,
+                                const int32_t* pair_index,
                                 int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12,
                                 float* second12, int32_t* nn21, float* best21, void* ws,
                                 size_t ws_bytes, void* stream_) {
@@ -328,8 +329,11 @@ extern "C" int sslam_match_top2(const void* bank1, const void* bank2, const int3
   SSLAM_REQUIRE(D % 4 == 0 && D <= MAX_D, SSLAM_EUNSUPPORTED, "match: D=%d (need D%%4==0, D<=256)", D);
   SSLAM_REQUIRE(dtype == SSLAM_SIM_F32 || dtype == SSLAM_SIM_TF32X3 || dtype == SSLAM_SIM_BF16,
                 SSLAM_EINVAL, "match: unknown dtype %d", dtype);
-  SSLAM_REQUIRE(ws_bytes >= sslam_match_workspace_bytes(P, N, M, D, dtype), SSLAM_EWORKSPACE,
-                "match: workspace %zu < %zu", ws_bytes, sslam_match_workspace_bytes(P, N, M, D, dtype));
+  SSLAM_REQUIRE(F1 > 0 && F2 > 0 && (pair_index || (F1 >= P && F2 >= P)), SSLAM_EINVAL,
+                "match: banks hold %d / %d sets but %d implicit pairs were requested", F1, F2, P);
+  SSLAM_REQUIRE(ws_bytes >= sslam_match_workspace_bytes(F1, F2, P, N, M, D, dtype), SSLAM_EWORKSPACE,
+                "match: workspace %zu < %zu", ws_bytes,
+                sslam_match_workspace_bytes(F1, F2, P, N, M, D, dtype));
   SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(bank1) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(bank2) & 15) == 0, SSLAM_EINVAL,
                 "match: descriptor banks must be 16-byte aligned");
@@ -354,7 +358,7 @@ extern "C" int sslam_match_top2(const void* bank1, const void* bank2, const int3
     match_f32_kernel<<<grid, THREADS, smem, stream>>>(mp);
     SSLAM_LAUNCHED();
   } else {
-    rc = match_top2_tc(bank1, bank2, pair_index, dtype, P, N, M, D, nn12, best12, second12, colkeys,
+    rc = match_top2_tc(bank1, F1, bank2, F2, pair_index, dtype, P, N, M, D, nn12, best12, second12, colkeys,
                        reinterpret_cast<char*>(ws) + colbytes, ws_bytes - colbytes, stream);
     if (rc) return rc;
   }

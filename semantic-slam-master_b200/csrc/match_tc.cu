@@ -1,14 +1,378 @@
-// tcgen05 / TMEM / TMA similarity kernel — placeholder until the tensor-core path lands.
-#include "common.cuh"
+// Tensor-core similarity with the top-2 / argmax epilogue fused in: tcgen05.mma accumulating in
+// TMEM, operands staged by TMA into 128B-swizzled shared memory, mbarrier pipelines, no similarity
+// matrix in HBM.
+//
+//   SSLAM_SIM_BF16   : S = A.B^T on bf16 copies (kind::f16), fp32 accumulate.
+//   SSLAM_SIM_TF32X3 : "fp32 mode".  Each fp32 operand x is split into hi = tf32(x) and
+//                      lo = tf32(x - hi) (both round-to-nearest, so hi + lo carries ~22 mantissa
+//                      bits) and S = Ah.Bh + Ah.Bl + Al.Bh with kind::tf32, fp32 accumulate in TMEM.
+//                      The dropped Al.Bl term is <= 2^-22 |a||b|; against the exact-mode kernel the
+//                      decisions are identical except for similarity near-ties (< 1e-6), which the
+//                      parity tests count.
+//
+// CTA = one 128-row strip of one pair; it walks the column tiles (128 wide) of the pair:
+//   warp 0      TMA producer   : per k-block (128 bytes of K) loads the A and B tiles of every term
+//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma; tcgen05.commit releases the
+//                                smem stage and, after the last k-block, publishes the accumulator
+//   warps 2..5  epilogue       : tcgen05.ld the 128x128 fp32 tile (thread = row), update the row's
+//                                running (best, index, second), reduce each column over the 128 rows
+//                                (redux.sync max + ballot) and merge column results across strips with
+//                                a 64-bit atomicMax on (ordered value << 32 | ~row)
+// Two accumulators (2 x 128 TMEM columns) let the epilogue of tile t overlap the MMAs of tile t+1.
+#include "tc_common.cuh"
+
+#include <mutex>
 
 namespace sslam {
 
-size_t match_tc_extra_workspace(int, int, int, int, int) { return 0; }
+using namespace tc;
 
-int match_top2_tc(const void*, const void*, const int32_t*, int dtype, int, int, int, int, int32_t*,
-                  float*, float*, u64*, void*, size_t, cudaStream_t) {
-  set_error("match: dtype %d (tensor-core path) not built yet", dtype);
-  return SSLAM_EUNSUPPORTED;
+namespace {
+
+constexpr int BM = 128, BN = 128;
+constexpr int BLOCK_BYTES = BM * 128;            // one operand tile: 128 rows x 128 bytes of K
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 256;
+
+template <int MODE> struct Cfg;
+template <> struct Cfg<SSLAM_SIM_BF16> {
+  static constexpr int TERMS = 1, STAGES = 6, ELEM = 2, BK = 64, UMMA_K = 16;
+  static constexpr bool TF32 = false;
+};
+template <> struct Cfg<SSLAM_SIM_TF32X3> {
+  static constexpr int TERMS = 2, STAGES = 3, ELEM = 4, BK = 32, UMMA_K = 8;
+  static constexpr bool TF32 = true;
+};
+
+struct TcParams {
+  const int32_t* pair_index;
+  int P, N, M, D;
+  int32_t* nn12;
+  float* best12;
+  float* second12;
+  u64* colkeys;
+};
+
+template <int MODE>
+struct SmemLayout {
+  using C = Cfg<MODE>;
+  static constexpr int STAGE_BYTES = 2 * C::TERMS * BLOCK_BYTES;     // A terms then B terms
+  static constexpr int OPERANDS = C::STAGES * STAGE_BYTES;
+  static constexpr int COLPART = 2 * 4 * BN * 8;                     // [acc][warp][col] u64
+  static constexpr int BARS = (2 * C::STAGES + 4) * 8 + 16;
+  static constexpr int TOTAL = OPERANDS + COLPART + BARS + 1024;     // + alignment slack
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                TcParams p) {
+  using C = Cfg<MODE>;
+  using L = SmemLayout<MODE>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* operands = smem;
+  u64* colpart = reinterpret_cast<u64*>(smem + L::OPERANDS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OPERANDS + L::COLPART);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strips = (p.N + BM - 1) / BM;
+  const int pair = blockIdx.x / strips;
+  const int strip = blockIdx.x - pair * strips;
+  int ia = pair, ib = pair;
+  if (p.pair_index) { ia = p.pair_index[2 * pair]; ib = p.pair_index[2 * pair + 1]; }
+  const int row0 = strip * BM;
+  const int a_row = ia * p.N + row0;           // row coordinate in the [F*N, D] tensor map
+  const int b_row0 = ib * p.M;
+  const int ntile = (p.M + BN - 1) / BN;
+  const int nkb = (p.D + C::BK - 1) / C::BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmB_hi);
+      if (C::TERMS == 2) { prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_lo); }
+      int stage = 0; uint32_t phase = 0;
+      for (int ct = 0; ct < ntile; ++ct) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = operands + stage * L::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+          const int kc = kb * C::BK;
+          tma_load_2d(st, &tmA_hi, &full[stage], kc, a_row);
+          if (C::TERMS == 2) tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, a_row);
+          tma_load_2d(st + C::TERMS * BLOCK_BYTES, &tmB_hi, &full[stage], kc, b_row0 + ct * BN);
+          if (C::TERMS == 2)
+            tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, b_row0 + ct * BN);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_instr_desc(C::TF32 ? FMT_TF32 : FMT_BF16, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      for (int ct = 0; ct < ntile; ++ct) {
+        const int acc = ct & 1;
+        const uint32_t acc_phase = (ct >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_phase ^ 1);                 // epilogue drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);                       // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(operands + stage * L::STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc_sw128(sa);
+          const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
+          const uint64_t b_hi = make_smem_desc_sw128(sa + C::TERMS * BLOCK_BYTES);
+          const uint64_t b_lo = make_smem_desc_sw128(sa + 3 * BLOCK_BYTES);
+#pragma unroll
+          for (int k = 0; k < 128 / 32; ++k) {                  // 32 bytes of K per instruction
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t first = (kb | k) ? 1u : 0u;
+            if (C::TERMS == 2) {
+              umma_ss<C::TF32>(tmem_d, a_lo + adv, b_hi + adv, idesc, first);   // small terms first
+              umma_ss<C::TF32>(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_ss<C::TF32>(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+            } else {
+              umma_ss<C::TF32>(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+            }
+          }
+          tcgen05_commit(&empty[stage]);                        // smem stage reusable when MMAs retire
+          if (kb == nkb - 1) tcgen05_commit(&tfull[acc]);       // accumulator complete
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;                                     // TMEM lane quarter of this warp
+    const int ew = warp - 2;                                    // 0..3, slot in colpart
+    const int et = threadIdx.x - 64;                            // 0..127
+    const int grow = row0 + q * 32 + lane;                      // global row of this thread
+    const bool row_ok = grow < p.N;
+    const float NEG_INF = __int_as_float(0xff800000);
+    float best = NEG_INF, second = NEG_INF;
+    int bidx = 0x7fffffff;
+    for (int ct = 0; ct < ntile; ++ct) {
+      const int acc = ct & 1;
+      const uint32_t acc_phase = (ct >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tcgen05_fence_after();
+      u64* cp = colpart + (acc * 4 + ew) * BN;
+      const int c0 = ct * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, r);
+        tmem_ld_wait();
+        u64 mykey = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float v = __uint_as_float(r[j]);
+          const int gc = c0 + ch * 32 + j;
+          if (gc < p.M) {                                       // warp-uniform
+            // row: columns arrive in ascending order, strict '>' keeps the lowest index
+            if (v > best) { second = best; best = v; bidx = gc; }
+            else second = fmaxf(second, v);
+            // column: maximum over the 32 rows of this warp, lowest row on ties
+            const uint32_t ov = row_ok ? ordered_from_float(v) : 0u;
+            const uint32_t mx = __reduce_max_sync(0xffffffffu, ov);
+            const uint32_t bal = __ballot_sync(0xffffffffu, ov == mx);
+            if (lane == j && mx != 0u)
+              mykey = ((u64)mx << 32) | (u64)(0xffffffffu - (uint32_t)(row0 + q * 32 + (__ffs(bal) - 1)));
+          }
+        }
+        cp[ch * 32 + lane] = mykey;
+      }
+      // accumulator fully read: hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      // merge the four warps' column results and publish
+      named_bar_sync(1, 128);
+      {
+        const u64* base = colpart + acc * 4 * BN;
+        u64 k = base[et];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) { u64 o = base[w * BN + et]; k = o > k ? o : k; }
+        if (c0 + et < p.M && k) atomicMax(p.colkeys + (size_t)pair * p.M + c0 + et, k);
+      }
+    }
+    if (row_ok) {
+      const size_t o = (size_t)pair * p.N + grow;
+      p.nn12[o] = bidx; p.best12[o] = best; p.second12[o] = second;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// fp32 -> (tf32 hi, tf32 lo) split of a descriptor bank
+__global__ void split_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ hi,
+                                  float4* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 x = __ldg(src + i), h, l;
+    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+    l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
+    l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_encode_once;
+
+}  // namespace
+
+namespace tc {
+int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
+                       uint32_t box_rows, uint32_t box_cols, int elem_bytes) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  SSLAM_REQUIRE(g_encode != nullptr, SSLAM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSLAM_REQUIRE(r == CUDA_SUCCESS, SSLAM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SSLAM_OK;
+}
+}  // namespace tc
+
+namespace {
+
+// When bank2 lies inside / directly after bank1 on a frame boundary (sequence mode: bank2 =
+// bank1 + one frame) the two banks are split once, over their union.
+struct BankPlan {
+  bool shared;           // one split region serves both banks
+  size_t frames_a, frames_b, off_b_frames;
+};
+
+BankPlan plan_banks(const float* b1, int F1, const float* b2, int F2, int N, int M, int D) {
+  BankPlan pl{false, (size_t)F1, (size_t)F2, 0};
+  if (N != M) return pl;
+  const size_t frame = (size_t)N * D;
+  const float* end1 = b1 + (size_t)F1 * frame;
+  if (b2 >= b1 && b2 <= end1 && ((size_t)(b2 - b1) % frame) == 0) {
+    pl.shared = true;
+    pl.off_b_frames = (size_t)(b2 - b1) / frame;
+    size_t uni = pl.off_b_frames + (size_t)F2;
+    pl.frames_a = uni > (size_t)F1 ? uni : (size_t)F1;
+  }
+  return pl;
+}
+
+}  // namespace
+
+size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype, int F1, int F2) {
+  (void)P;
+  if (dtype != SSLAM_SIM_TF32X3) return 0;
+  // worst case: both banks split separately (hi + lo each)
+  return 2 * align_up((size_t)F1 * N * D * 4, 256) + 2 * align_up((size_t)F2 * M * D * 4, 256) + 1024;
+}
+
+template <int MODE>
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                     const CUtensorMap& b_lo, const TcParams& tp, cudaStream_t stream) {
+  using L = SmemLayout<MODE>;
+  static std::atomic<bool> configured{false};
+  if (!configured.load()) {
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(match_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          L::TOTAL));
+    configured.store(true);
+  }
+  const int strips = (tp.N + BM - 1) / BM;
+  match_tc_kernel<MODE><<<strips * tp.P, NUM_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}
+
+int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
+                  int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
+                  u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream) {
+  TcParams tp;
+  tp.pair_index = pair_index; tp.P = P; tp.N = N; tp.M = M; tp.D = D;
+  tp.nn12 = nn12; tp.best12 = best12; tp.second12 = second12; tp.colkeys = colkeys;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
+  int rc;
+  if (dtype == SSLAM_SIM_BF16) {
+    SSLAM_REQUIRE(D % 8 == 0, SSLAM_EUNSUPPORTED, "match(bf16): D=%d must be a multiple of 8", D);
+    if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, bank2, (uint64_t)F2 * M, D, BN, 64, 2))) return rc;
+    a_lo = a_hi; b_lo = b_hi;
+    return launch_tc<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
+  }
+  // ---- tf32x3: split the fp32 banks into hi / lo
+  SSLAM_REQUIRE(ws_extra_bytes >= match_tc_extra_workspace(P, N, M, D, dtype, F1, F2), SSLAM_EWORKSPACE,
+                "match(tf32x3): workspace too small");
+  const float* f1 = static_cast<const float*>(bank1);
+  const float* f2 = static_cast<const float*>(bank2);
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws_extra) + 1023) & ~(uintptr_t)1023);
+  const BankPlan pl = plan_banks(f1, F1, f2, F2, N, M, D);
+  const size_t n1 = pl.frames_a * (size_t)N * D;
+  float* h1 = reinterpret_cast<float*>(w);
+  float* l1 = reinterpret_cast<float*>(w + align_up(n1 * 4, 256));
+  const int sms = num_sms();
+  split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f1),
+                                                 reinterpret_cast<float4*>(h1), reinterpret_cast<float4*>(l1), n1 / 4);
+  SSLAM_LAUNCHED();
+  float *h2, *l2;
+  uint64_t rows2;
+  if (pl.shared) {
+    h2 = h1 + pl.off_b_frames * (size_t)N * D;
+    l2 = l1 + pl.off_b_frames * (size_t)N * D;
+    rows2 = (uint64_t)F2 * M;
+  } else {
+    const size_t n2 = (size_t)F2 * M * D;
+    char* w2 = w + 2 * align_up(n1 * 4, 256);
+    h2 = reinterpret_cast<float*>(w2);
+    l2 = reinterpret_cast<float*>(w2 + align_up(n2 * 4, 256));
+    split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f2),
+                                                   reinterpret_cast<float4*>(h2), reinterpret_cast<float4*>(l2), n2 / 4);
+    SSLAM_LAUNCHED();
+    rows2 = (uint64_t)F2 * M;
+  }
+  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, 32, 4))) return rc;
+  return launch_tc<SSLAM_SIM_TF32X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
 }
 
 }  // namespace sslam

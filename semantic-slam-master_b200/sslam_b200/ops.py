@@ -146,9 +146,11 @@ def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, work
                second12=torch.empty(P, N, dtype=torch.float32, device=dev),
                nn21=torch.empty(P, M, dtype=torch.int32, device=dev),
                best21=torch.empty(P, M, dtype=torch.float32, device=dev))
-    need = lib.sslam_match_workspace_bytes(P, N, M, D, mode)
+    F1 = bank1.numel() // (N * D)
+    F2 = bank2.numel() // (M * D)
+    need = lib.sslam_match_workspace_bytes(F1, F2, P, N, M, D, mode)
     ws = workspace if workspace is not None else _ws("match", need, dev)
-    _lib.check(lib.sslam_match_top2(_ptr(bank1), _ptr(bank2), _ptr(pair_index), int(mode), P, N, M,
+    _lib.check(lib.sslam_match_top2(_ptr(bank1), F1, _ptr(bank2), F2, _ptr(pair_index), int(mode), P, N, M,
                                     D, _ptr(res["nn12"]), _ptr(res["best12"]), _ptr(res["second12"]),
                                     _ptr(res["nn21"]), _ptr(res["best21"]), _ptr(ws), ws.numel(),
                                     _stream()))
