@@ -1,0 +1,154 @@
+"""GPU parity of the tensor-core similarity kernels (tcgen05 / TMEM / TMA) against the oracle.
+
+fp32 mode (SSLAM_SIM_TF32X3): match index pairs identical to the oracle except similarity
+near-ties < 1e-6 (counted); similarity values within 2e-6 abs.
+bf16 mode (SSLAM_SIM_BF16): similarity values within 1e-5 abs of the fp64 product of the same
+bf16-rounded inputs, indices identical except near ties of that product; against the fp32 oracle on
+the un-rounded inputs the scores agree to bf16 input rounding.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import recipes
+from parity import compare_matches
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(128, 128, 256), (130, 257, 32), (2048, 2048, 256), (1, 5, 64), (300, 1, 64), (77, 129, 96),
+         (500, 500, 128)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def cu(x, dev):
+    return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+def check_top(t, S64, tol_val, tol_tie):
+    n, m = S64.shape
+    nn12 = S64.argmax(1)
+    nn21 = S64.argmax(0)
+    best12 = S64[np.arange(n), nn12]
+    best21 = S64[nn21, np.arange(m)]
+    assert np.abs(t["best12"] - best12).max() <= tol_val
+    assert np.abs(t["best21"] - best21).max() <= tol_val
+    if m > 1:
+        second = -np.partition(-S64, 1, axis=1)[:, 1]
+        assert np.abs(t["second12"] - second).max() <= tol_val
+    else:
+        assert np.isneginf(t["second12"]).all()
+    exc = 0
+    for i in np.nonzero(t["nn12"] != nn12)[0]:
+        assert abs(S64[i, t["nn12"][i]] - S64[i, nn12[i]]) < tol_tie, "row argmax differs beyond a near tie"
+        exc += 1
+    for j in np.nonzero(t["nn21"] != nn21)[0]:
+        assert abs(S64[t["nn21"][j], j] - S64[nn21[j], j]) < tol_tie, "column argmax differs beyond a near tie"
+        exc += 1
+    return exc
+
+
+@pytest.mark.parametrize("n,m,d", CASES)
+def test_tf32x3_top2(n, m, d, dev):
+    from sslam_b200 import ops
+    d1, d2, _ = recipes.descriptor_pair(n, m, d, 300 + n + m, noise=3, dup_every=11)
+    top = ops.match_top2(cu(d1[None], dev), cu(d2[None], dev), mode=ops.SIM_TF32X3)
+    t = {k: v[0].cpu().numpy() for k, v in top.items()}
+    S64 = d1.astype(np.float64) @ d2.astype(np.float64).T
+    exc = check_top(t, S64, 2e-6, 1e-6)
+    print(f"tf32x3 {n}x{m}x{d}: near-tie index exceptions {exc}, "
+          f"max |best-S| {np.abs(t['best12'] - S64.max(1)).max():.2e}")
+
+
+@pytest.mark.parametrize("n,m,d", [c for c in CASES if c[2] % 8 == 0])
+def test_bf16_top2(n, m, d, dev):
+    from sslam_b200 import ops
+    d1, d2, _ = recipes.descriptor_pair(n, m, d, 400 + n + m, noise=3)
+    b1 = cu(d1[None], dev).to(torch.bfloat16)
+    b2 = cu(d2[None], dev).to(torch.bfloat16)
+    top = ops.match_top2(b1, b2, mode=ops.SIM_BF16)
+    t = {k: v[0].cpu().numpy() for k, v in top.items()}
+    S64 = b1[0].double().cpu().numpy() @ b2[0].double().cpu().numpy().T
+    check_top(t, S64, 1e-5, 1e-5)
+    _, best12, *_ = oracle.similarity_top2(d1, d2)
+    rel = np.abs(t["best12"] - best12) / np.maximum(np.abs(best12), 1e-3)
+    assert rel.max() < 1e-2, rel.max()          # bf16 input rounding: 2^-9 per operand
+    print(f"bf16 {n}x{m}x{d}: max rel err vs fp32 oracle {rel.max():.2e}")
+
+
+def test_tc_pair_index_and_aliasing(dev):
+    """Sequence-style aliasing (bank2 = bank1[1:]) and explicit pair lists, both modes."""
+    from sslam_b200 import ops
+    F, N, D = 5, 200, 64
+    bank = np.stack([recipes.descriptor_pair(N, N, D, 500 + f, noise=2)[f % 2] for f in range(F)])
+    b32 = cu(bank, dev)
+    ref = ops.match_top2(b32, b32[1:], mode=ops.SIM_F32, num_pairs=F - 1)
+    for mode, bk in ((ops.SIM_TF32X3, b32), (ops.SIM_BF16, b32.to(torch.bfloat16))):
+        top = ops.match_top2(bk, bk[1:], mode=mode, num_pairs=F - 1)
+        tol = 2e-6 if mode == ops.SIM_TF32X3 else 2e-2
+        assert torch.allclose(top["best12"], ref["best12"], atol=tol, rtol=0)
+        assert torch.allclose(top["best21"], ref["best21"], atol=tol, rtol=0)
+        if mode == ops.SIM_TF32X3:
+            agree = (top["nn12"] == ref["nn12"]).float().mean().item()
+            assert agree > 0.999
+        idx = torch.tensor([[4, 0], [2, 2], [0, 3]], dtype=torch.int32, device=dev)
+        a = ops.match_top2(bk, bk, pair_index=idx, mode=mode)
+        r = ops.match_top2(b32, b32, pair_index=idx, mode=ops.SIM_F32)
+        assert torch.allclose(a["best12"], r["best12"], atol=tol, rtol=0)
+
+
+def test_tf32x3_sequence_matches_vs_oracle(dev):
+    """c2-shaped: 3 frames 640x480, K=2048, D=256, consecutive pairs, fp32 (tf32x3) mode."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, ops, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    T, K = 3, 2048
+    sal, feat = synth.make_sequence(T, seq_id=1)
+    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel", sim_mode=ops.SIM_TF32X3)
+    feats, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1)
+    d = feats["descriptors"].cpu().numpy()
+    sc = feats["scores"].cpu().numpy()
+    p2, q2, c2 = fe.match_consecutive(feats, matchers.M2)
+    exc = 0
+    for p in range(T - 1):
+        S = d[p].astype(np.float64) @ d[p + 1].astype(np.float64).T
+        ref = oracle.match_m1(d[p], d[p + 1], 0.8)
+        got = pairs[p, :int(counts[p])].cpu().numpy()
+        exc += compare_matches(S, np.array([(i, j) for i, j, _ in ref]).reshape(-1, 2), got)
+        rm, rq = oracle.match_m2(d[p], d[p + 1], sc[p], sc[p + 1])
+        exc += compare_matches(S, rm, p2[p, :int(c2[p])].cpu().numpy(),
+                               threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
+        assert int(counts[p]) > K // 4
+    print("tf32x3 sequence near-tie exceptions:", exc)
+
+
+def test_bf16_sequence_scores(dev):
+    """c3-shaped slice: K=4096, bf16 similarity, ratio test 0.8 (M1)."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, ops, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    sal, feat = synth.make_sequence(2, seq_id=2)
+    fe = FrontEnd(refiner, num_keypoints=4096, grid="pixel", sim_mode=ops.SIM_BF16)
+    feats, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1)
+    d = feats["descriptors"].cpu().numpy()
+    ref = oracle.match_m1(d[0], d[1], 0.8)
+    refd = {(i, j): s for i, j, s in ref}
+    n = int(counts[0])
+    got = pairs[0, :n].cpu().numpy()
+    gs = pscores[0, :n].cpu().numpy()
+    common = [(k, refd[tuple(r)]) for k, r in enumerate(got.tolist()) if tuple(r) in refd]
+    agree = len(common) / max(len(ref), 1)
+    rel = max(abs(gs[k] - s) / abs(s) for k, s in common)
+    print(f"bf16 K=4096: index agreement {100 * agree:.2f}% of {len(ref)} matches, max rel score err {rel:.2e}")
+    assert agree > 0.98
+    assert rel < 1e-2
