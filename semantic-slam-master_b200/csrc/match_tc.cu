@@ -19,9 +19,12 @@
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma; tcgen05.commit releases the
 //                                smem stage and, after the last k-block, publishes the accumulator
 //   warps 2..5  epilogue       : tcgen05.ld the 128x128 fp32 tile (thread = row), update the row's
-//                                running (best, index, second), reduce each column over the 128 rows
-//                                (redux.sync max + ballot) and merge column results across strips with
-//                                a 64-bit atomicMax on (ordered value << 32 | ~row)
+//                                running (best, index, second); for the column argmax each warp
+//                                transposes its 32x32 chunk through a padded smem tile so that lane j
+//                                scans column j over the warp's 32 rows (no cross-lane reductions:
+//                                redux.sync turned out to cost ~16k cycles per tile), then the four
+//                                warps' results are merged and published across strips with a 64-bit
+//                                atomicMax on (ordered value << 32 | ~row)
 // Two accumulator sets (bf16: 2 x 128 TMEM columns; tf32x3: 2 x (128 + 128)) let the epilogue of
 // tile t overlap the MMAs of tile t+1.
 #include "tc_common.cuh"
@@ -37,6 +40,7 @@ namespace {
 constexpr int BM = 128, BN = 128;
 constexpr int BLOCK_BYTES = BM * 128;            // one operand tile: 128 rows x 128 bytes of K
 constexpr int NUM_THREADS = 192;
+constexpr int TP_LD = 36;                        // padded row length (floats) of the transpose tile
 
 template <int MODE> struct Cfg;
 template <> struct Cfg<SSLAM_SIM_BF16> {
@@ -63,8 +67,9 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = 2 * C::TERMS * BLOCK_BYTES;     // A terms then B terms
   static constexpr int OPERANDS = C::STAGES * STAGE_BYTES;
   static constexpr int COLPART = 2 * 4 * BN * 8;                     // [acc][warp][col] u64
+  static constexpr int TRANSP = 4 * 32 * TP_LD * 4;                  // [warp][32 rows][TP_LD] fp32
   static constexpr int BARS = (2 * C::STAGES + 4) * 8 + 16;
-  static constexpr int TOTAL = OPERANDS + COLPART + BARS + 1024;     // + alignment slack
+  static constexpr int TOTAL = OPERANDS + COLPART + TRANSP + BARS + 1024;   // + alignment slack
 };
 
 template <int MODE>
@@ -79,7 +84,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   unsigned char* operands = smem;
   u64* colpart = reinterpret_cast<u64*>(smem + L::OPERANDS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OPERANDS + L::COLPART);
+  float* transp = reinterpret_cast<float*>(smem + L::OPERANDS + L::COLPART);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OPERANDS + L::COLPART + L::TRANSP);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
   uint64_t* tfull = bars + 2 * C::STAGES;
@@ -175,6 +181,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int et = threadIdx.x - 64;                            // 0..127
     const int grow = row0 + q * 32 + lane;                      // global row of this thread
     const bool row_ok = grow < p.N;
+    float* tp = transp + ew * 32 * TP_LD;
+    int nvalid = p.N - (row0 + q * 32);                         // valid rows of this warp (uniform)
+    nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
     const float NEG_INF = __int_as_float(0xff800000);
     float best = NEG_INF, second = NEG_INF;
     int bidx = 0x7fffffff;
@@ -200,24 +209,42 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         } else {
           tmem_ld_wait();
         }
-        u64 mykey = 0;
+        // row: columns arrive in ascending order, strict '>' keeps the lowest index
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]);
           const int gc = c0 + ch * 32 + j;
           if (gc < p.M) {                                       // warp-uniform
-            // row: columns arrive in ascending order, strict '>' keeps the lowest index
             if (v > best) { second = best; best = v; bidx = gc; }
             else second = fmaxf(second, v);
-            // column: maximum over the 32 rows of this warp, lowest row on ties
-            const uint32_t ov = row_ok ? ordered_from_float(v) : 0u;
-            const uint32_t mx = __reduce_max_sync(0xffffffffu, ov);
-            const uint32_t bal = __ballot_sync(0xffffffffu, ov == mx);
-            if (lane == j && mx != 0u)
-              mykey = ((u64)mx << 32) | (u64)(0xffffffffu - (uint32_t)(row0 + q * 32 + (__ffs(bal) - 1)));
           }
         }
-        cp[ch * 32 + lane] = mykey;
+        // column: transpose the 32x32 chunk through smem, lane j scans column j top-down
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(tp + lane * TP_LD + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+        __syncwarp();
+        float cm = 0.f;
+        int cr = -1;
+        if (nvalid == 32) {                                     // two independent chains, merged
+          float m0 = tp[lane], m1 = tp[16 * TP_LD + lane];
+          int r0 = 0, r1 = 16;
+#pragma unroll
+          for (int rr = 1; rr < 16; ++rr) {                     // rows ascending: lowest row wins ties
+            const float v0 = tp[rr * TP_LD + lane], v1 = tp[(16 + rr) * TP_LD + lane];
+            if (v0 > m0) { m0 = v0; r0 = rr; }
+            if (v1 > m1) { m1 = v1; r1 = 16 + rr; }
+          }
+          cm = m0; cr = r0;
+          if (m1 > m0) { cm = m1; cr = r1; }
+        } else {
+          for (int rr = 0; rr < nvalid; ++rr) {
+            const float v = tp[rr * TP_LD + lane];
+            if (cr < 0 || v > cm) { cm = v; cr = rr; }
+          }
+        }
+        cp[ch * 32 + lane] = (cr >= 0) ? pack_key(cm, (u32)(row0 + q * 32 + cr)) : 0ull;
       }
       // accumulator fully read: hand it back to the MMA warp
       tcgen05_fence_before();
