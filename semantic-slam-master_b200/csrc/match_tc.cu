@@ -80,8 +80,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   using C = Cfg<MODE>;
   using L = SmemLayout<MODE>;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment for SWIZZLE_128B; offset arithmetic keeps the pointer in the shared space
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* operands = smem;
   u64* colpart = reinterpret_cast<u64*>(smem + L::OPERANDS);
   float* transp = reinterpret_cast<float*>(smem + L::OPERANDS + L::COLPART);
@@ -209,15 +209,20 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         } else {
           tmem_ld_wait();
         }
-        // row: columns arrive in ascending order, strict '>' keeps the lowest index
+        // row: columns arrive in ascending order, strict '>' keeps the lowest index (branch-free)
+        const int gc0 = c0 + ch * 32;
+        if (gc0 + 32 > p.M) {                                   // ragged last tile (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gc0 + j >= p.M) r[j] = 0xff800000u;             // -inf never wins, never second
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float v = __uint_as_float(r[j]);
-          const int gc = c0 + ch * 32 + j;
-          if (gc < p.M) {                                       // warp-uniform
-            if (v > best) { second = best; best = v; bidx = gc; }
-            else second = fmaxf(second, v);
-          }
+          const bool gt = v > best;
+          second = gt ? best : fmaxf(second, v);
+          bidx = gt ? (gc0 + j) : bidx;
+          best = gt ? v : best;
         }
         // column: transpose the 32x32 chunk through smem, lane j scans column j top-down
         __syncwarp();

@@ -59,16 +59,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
   for (uint32_t spin = 0; !ok; ++spin) {
+    // the suspend-time hint lets the hardware park the thread instead of spinning on issue slots
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
         : "memory");
-    if (!ok && spin > (1u << 26)) __trap();
+    if (!ok && spin > (1u << 22)) __trap();
   }
 }
 
