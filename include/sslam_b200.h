@@ -117,6 +117,27 @@ int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f3
                       void* out_bf16, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * DescriptorRefiner forward (models/descriptor_refiner.py:58-91, 108-126): Linear+ReLU, `blocks`
+ * pre-LayerNorm residual blocks, Linear, L2 normalise — tcgen05 tf32x3 GEMMs (fp32-level accuracy)
+ * with fused bias / residual / ReLU epilogues.
+ *   params : HOST array of 4 + 8*blocks DEVICE pointers (fp32), in state_dict order:
+ *            input_proj.{weight [Hd,C], bias}; per block norm1.{weight,bias}, fc1.{weight [Hd,Hd],
+ *            bias}, norm2.{weight,bias}, fc2.{weight,bias}; output_proj.{weight [D,Hd], bias}
+ *   packed : device buffer of sslam_refiner_packed_bytes(), filled once per weight set by
+ *            sslam_refiner_pack_weights() (tf32 hi/lo copies of the Linear weights)
+ *   x [rows,C] fp32 -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16, unit L2 norm
+ * C, Hd, D multiples of 4; Hd <= 1024; LayerNorm eps is torch's default 1e-5.
+ */
+size_t sslam_refiner_packed_bytes(int C, int Hd, int D, int blocks);
+int sslam_refiner_pack_weights(const float* const* params, int C, int Hd, int D, int blocks,
+                               void* packed, size_t packed_bytes, void* stream);
+size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks);
+int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
+                              int rows, int C, int Hd, int D, int blocks, float eps_norm,
+                              float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
+                              void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Matching primitive shared by M1..M5: over the virtual S_p = D1_p . D2_p^T (never stored)
  *   per row    nn12 (lowest argmax), best12, second12 (second entry of the row sorted descending,
  *              -inf when M == 1);     [P,N]

@@ -1,0 +1,414 @@
+// DescriptorRefiner forward on tensor cores.
+//
+// Replaces the body of DescriptorRefiner.forward / ResidualBlock.forward
+// (models/descriptor_refiner.py:73-86, 108-126): Linear+ReLU, [LN, Linear+ReLU, LN, Linear,
+// +identity, ReLU] x blocks, Linear, L2 normalise — with fp32-level accuracy:
+//
+//   * every Linear is a tcgen05 kind::tf32 GEMM in the 3-term hi/lo split
+//     (x = hi + lo, both round-to-nearest tf32;  x.w ~= hi.hi' + hi.lo' + lo.hi'), operands fed by
+//     TMA into 128B-swizzled smem, accumulators in TMEM.  As in match_tc.cu the small cross terms
+//     get their own accumulator so that the tensor core's truncating accumulate does not eat them.
+//   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes
+//     either fp32 or the (hi, lo) pair the next GEMM consumes, through a smem transpose so that
+//     global stores are 128-byte coalesced.
+//   * LayerNorm is a warp-per-row kernel that reads fp32 and writes the (hi, lo) pair.
+//
+// One CTA = a 128-row strip; it walks the N/128 column tiles of the layer.  Activations round-trip
+// HBM between layers (rows x 384 fp32); the whole chain is ~10 launches per call.
+#include "tc_common.cuh"
+
+namespace sslam {
+
+using namespace tc;
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 32;               // BK fp32 = 128 bytes of K
+constexpr int BLOCK_BYTES = BM * 128;
+constexpr int STAGES = 3;
+constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int NUM_THREADS = 192;
+constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 cross)
+constexpr int TP_LD = 36;
+constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
+constexpr int SMEM_TRANSP = 4 * 32 * TP_LD * 4;
+constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_BARS + 1024;
+
+struct GemmParams {
+  int rows, N, K;
+  const float* bias;        // [N]
+  const float* residual;    // [rows, N] or null
+  int relu;
+  float* out_f32;           // [rows, N] or null
+  float* out_hi;            // [rows, N] or null (with out_lo)
+  float* out_lo;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                   GemmParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* operands = smem;
+  float* transp = reinterpret_cast<float*>(smem + SMEM_OPERANDS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * BM;
+  const int ntile = (p.N + BN - 1) / BN;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {                                            // ---- TMA producer
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
+      prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+      int stage = 0; uint32_t phase = 0;
+      for (int ct = 0; ct < ntile; ++ct) {
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = operands + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+          const int kc = kb * BK;
+          tma_load_2d(st, &tmA_hi, &full[stage], kc, row0);
+          tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, row0);
+          tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, ct * BN);
+          tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, ct * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {                                            // ---- MMA issuer
+      const uint32_t idesc = make_instr_desc(FMT_TF32, BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      for (int ct = 0; ct < ntile; ++ct) {
+        const int acc = ct & 1;
+        mbar_wait(&tempty[acc], ((ct >> 1) & 1) ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+        const uint32_t tmem_s = tmem_d + BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(operands + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc_sw128(sa);
+          const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
+          const uint64_t b_hi = make_smem_desc_sw128(sa + 2 * BLOCK_BYTES);
+          const uint64_t b_lo = make_smem_desc_sw128(sa + 3 * BLOCK_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t first = (kb | k) ? 1u : 0u;
+            umma_ss<true>(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
+            umma_ss<true>(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_ss<true>(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+          }
+          tcgen05_commit(&empty[stage]);
+          if (kb == nkb - 1) tcgen05_commit(&tfull[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..5: TMEM -> (+bias, +residual, relu) -> smem transpose -> coalesced stores
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    float* tp = transp + ew * 32 * TP_LD;
+    const int wrow0 = row0 + q * 32;                    // first global row of this warp
+    const int sub_r = lane >> 3;                        // store mapping: 8 lanes per row, 4 rows per pass
+    const int sub_c = (lane & 7) * 4;
+    for (int ct = 0; ct < ntile; ++ct) {
+      const int acc = ct & 1;
+      mbar_wait(&tfull[acc], (ct >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32], rs[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + ch * 32;
+        tmem_ld_32x32(taddr, r);
+        tmem_ld_32x32(taddr + BN, rs);
+        tmem_ld_wait();
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 v;
+          v.x = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rs[j]));
+          v.y = __fadd_rn(__uint_as_float(r[j + 1]), __uint_as_float(rs[j + 1]));
+          v.z = __fadd_rn(__uint_as_float(r[j + 2]), __uint_as_float(rs[j + 2]));
+          v.w = __fadd_rn(__uint_as_float(r[j + 3]), __uint_as_float(rs[j + 3]));
+          *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
+        }
+        __syncwarp();
+        const int gc = ct * BN + ch * 32 + sub_c;       // first of this lane's 4 columns
+        if (gc < p.N) {                                 // N % 4 == 0
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int lr = pass * 4 + sub_r;
+            const int gr = wrow0 + lr;
+            if (gr < p.rows) {
+              float4 v = *reinterpret_cast<const float4*>(tp + lr * TP_LD + sub_c);
+              v.x = __fadd_rn(v.x, b4.x); v.y = __fadd_rn(v.y, b4.y);
+              v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
+              const size_t o = (size_t)gr * p.N + gc;
+              if (p.residual) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
+                v.x = __fadd_rn(v.x, rr.x); v.y = __fadd_rn(v.y, rr.y);
+                v.z = __fadd_rn(v.z, rr.z); v.w = __fadd_rn(v.w, rr.w);
+              }
+              if (p.relu) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              }
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (p.out_hi) {
+                float4 h, l;
+                h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
+                l.x = to_tf32_rna(__fsub_rn(v.x, h.x)); l.y = to_tf32_rna(__fsub_rn(v.y, h.y));
+                l.z = to_tf32_rna(__fsub_rn(v.z, h.z)); l.w = to_tf32_rna(__fsub_rn(v.w, h.w));
+                *reinterpret_cast<float4*>(p.out_hi + o) = h;
+                *reinterpret_cast<float4*>(p.out_lo + o) = l;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// fp32 [n] -> tf32 hi / lo
+__global__ void split_kernel(const float4* __restrict__ src, float4* __restrict__ hi,
+                             float4* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 x = __ldg(src + i), h, l;
+    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+    l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
+    l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+// LayerNorm over the last dim (torch.nn.LayerNorm, eps inside the sqrt, biased variance), one warp
+// per row, row held in registers (W <= 1024); writes the tf32 hi/lo pair for the next GEMM.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, int rows, int W, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, float* __restrict__ hi,
+                       float* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* src = x + (size_t)row * W;
+  float4 v[MAXV];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    v[i] = (c < W) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  sum = warp_reduce_sum(sum);
+  const float mean = sum / (float)W;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < W) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      sq += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  sq = warp_reduce_sum(sq);
+  const float rstd = 1.0f / sqrtf(sq / (float)W + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    if (c < W) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float4 y, h, l;
+      y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
+      y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
+      h.x = to_tf32_rna(y.x); h.y = to_tf32_rna(y.y); h.z = to_tf32_rna(y.z); h.w = to_tf32_rna(y.w);
+      l.x = to_tf32_rna(__fsub_rn(y.x, h.x)); l.y = to_tf32_rna(__fsub_rn(y.y, h.y));
+      l.z = to_tf32_rna(__fsub_rn(y.z, h.z)); l.w = to_tf32_rna(__fsub_rn(y.w, h.w));
+      *reinterpret_cast<float4*>(hi + (size_t)row * W + c) = h;
+      *reinterpret_cast<float4*>(lo + (size_t)row * W + c) = l;
+    }
+  }
+}
+
+int launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t stream) {
+  split_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                  reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n / 4);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}
+
+int launch_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int rows, int N,
+                int K, const float* bias, const float* residual, int relu, float* out_f32, float* out_hi,
+                float* out_lo, cudaStream_t stream) {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  int rc;
+  if ((rc = make_tensor_map_2d(&ta_hi, a_hi, rows, K, BM, BK, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&ta_lo, a_lo, rows, K, BM, BK, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_hi, w_hi, N, K, BN, BK, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_lo, w_lo, N, K, BN, BK, 4))) return rc;
+  static std::atomic<bool> configured{false};
+  if (!configured.load()) {
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          SMEM_TOTAL));
+    configured.store(true);
+  }
+  GemmParams gp;
+  gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
+  gp.out_f32 = out_f32; gp.out_hi = out_hi; gp.out_lo = out_lo;
+  gemm_tf32x3_kernel<<<(rows + BM - 1) / BM, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}
+
+int launch_layernorm(const float* x, int rows, int W, const float* g, const float* b, float* hi, float* lo,
+                     cudaStream_t stream) {
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  if (W <= 128) layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
+  else if (W <= 384) layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
+  else layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
+  SSLAM_LAUNCHED();
+  return SSLAM_OK;
+}
+
+// packed weights: for each Linear, hi then lo copies of the [out, in] matrix
+size_t packed_floats(int C, int Hd, int D, int blocks) {
+  return 2 * ((size_t)Hd * C + (size_t)blocks * 2 * Hd * Hd + (size_t)D * Hd);
+}
+
+}  // namespace
+}  // namespace sslam
+
+using namespace sslam;
+
+// params order (device pointers, fp32):
+//   [0] input_proj.weight [Hd,C]   [1] input_proj.bias [Hd]
+//   per block b (8 entries from 2 + 8b): norm1.weight, norm1.bias, fc1.weight [Hd,Hd], fc1.bias,
+//                                        norm2.weight, norm2.bias, fc2.weight [Hd,Hd], fc2.bias
+//   [2+8*blocks] output_proj.weight [D,Hd]   [3+8*blocks] output_proj.bias [D]
+extern "C" size_t sslam_refiner_packed_bytes(int C, int Hd, int D, int blocks) {
+  if (C <= 0 || Hd <= 0 || D <= 0 || blocks < 0) return 0;
+  return packed_floats(C, Hd, D, blocks) * sizeof(float);
+}
+
+extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int Hd, int D, int blocks,
+                                          void* packed, size_t packed_bytes, void* stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SSLAM_REQUIRE(params && packed, SSLAM_EINVAL, "refiner_pack: null pointer");
+  SSLAM_REQUIRE(C % 4 == 0 && Hd % 4 == 0 && D % 4 == 0, SSLAM_EUNSUPPORTED,
+                "refiner: dims must be multiples of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE(packed_bytes >= sslam_refiner_packed_bytes(C, Hd, D, blocks), SSLAM_EWORKSPACE,
+                "refiner_pack: packed buffer too small");
+  float* w = static_cast<float*>(packed);
+  auto pack = [&](const float* src, size_t n) -> int {
+    int r = launch_split(src, w, w + n, n, stream);
+    w += 2 * n;
+    return r;
+  };
+  if ((rc = pack(params[0], (size_t)Hd * C))) return rc;
+  for (int b = 0; b < blocks; ++b) {
+    if ((rc = pack(params[2 + 8 * b + 2], (size_t)Hd * Hd))) return rc;
+    if ((rc = pack(params[2 + 8 * b + 6], (size_t)Hd * Hd))) return rc;
+  }
+  return pack(params[2 + 8 * blocks], (size_t)D * Hd);
+}
+
+extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks) {
+  (void)blocks;
+  if (rows <= 0) return 0;
+  const size_t r = (size_t)rows;
+  // x_hi, x_lo [r,C]; h_a, h_b, u [r,Hd] fp32; t_hi, t_lo, o_hi, o_lo [r,Hd]; raw [r,D]
+  return (2 * r * C + 7 * r * Hd + r * D) * sizeof(float) + 10 * 256;
+}
+
+extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
+                                         int rows, int C, int Hd, int D, int blocks, float eps_norm,
+                                         float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
+                                         void* stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SSLAM_REQUIRE(rows >= 0, SSLAM_EINVAL, "refiner: negative rows");
+  if (rows == 0) return SSLAM_OK;
+  SSLAM_REQUIRE(params && packed && x && ws && (out_f32 || out_bf16), SSLAM_EINVAL, "refiner: null pointer");
+  SSLAM_REQUIRE(C % 4 == 0 && Hd % 4 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
+                "refiner: dims must be multiples of 4 and hidden <= 1024 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE(ws_bytes >= sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks), SSLAM_EWORKSPACE,
+                "refiner: workspace %zu < %zu", ws_bytes, sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks));
+  const size_t r = (size_t)rows;
+  char* wp = static_cast<char*>(ws);
+  auto take = [&](size_t floats) { float* q = reinterpret_cast<float*>(wp); wp += align_up(floats * 4, 256); return q; };
+  float* x_hi = take(r * C); float* x_lo = take(r * C);
+  float* h_a = take(r * Hd); float* h_b = take(r * Hd); float* u = take(r * Hd);
+  float* t_hi = take(r * Hd); float* t_lo = take(r * Hd);
+  float* o_hi = take(r * Hd); float* o_lo = take(r * Hd);     // operand pair of the output projection
+  float* raw = take(r * D);
+  const float* pk = static_cast<const float*>(packed);
+  auto next_w = [&](size_t n, const float*& hi, const float*& lo) { hi = pk; lo = pk + n; pk += 2 * n; };
+
+  const float *w_hi, *w_lo;
+  // input projection + ReLU                                              (descriptor_refiner.py:76)
+  if ((rc = launch_split(x, x_hi, x_lo, r * C, stream))) return rc;
+  next_w((size_t)Hd * C, w_hi, w_lo);
+  const bool no_blocks = (blocks == 0);
+  if ((rc = launch_gemm(x_hi, x_lo, w_hi, w_lo, rows, Hd, C, params[1], nullptr, 1,
+                        no_blocks ? nullptr : h_a, no_blocks ? o_hi : nullptr, no_blocks ? o_lo : nullptr, stream)))
+    return rc;
+  float* h_cur = h_a;
+  float* h_nxt = h_b;
+  for (int b = 0; b < blocks; ++b) {                                      // :79-80, :108-126
+    const float* const* bp = params + 2 + 8 * b;
+    if ((rc = launch_layernorm(h_cur, rows, Hd, bp[0], bp[1], t_hi, t_lo, stream))) return rc;
+    next_w((size_t)Hd * Hd, w_hi, w_lo);
+    if ((rc = launch_gemm(t_hi, t_lo, w_hi, w_lo, rows, Hd, Hd, bp[3], nullptr, 1, u, nullptr, nullptr, stream)))
+      return rc;
+    if ((rc = launch_layernorm(u, rows, Hd, bp[4], bp[5], t_hi, t_lo, stream))) return rc;
+    next_w((size_t)Hd * Hd, w_hi, w_lo);
+    const bool last = (b == blocks - 1);
+    // fc2 + identity + ReLU; the last block hands (hi, lo) straight to the output projection
+    if ((rc = launch_gemm(t_hi, t_lo, w_hi, w_lo, rows, Hd, Hd, bp[7], h_cur, 1, last ? nullptr : h_nxt,
+                          last ? o_hi : nullptr, last ? o_lo : nullptr, stream)))
+      return rc;
+    float* t = h_cur; h_cur = h_nxt; h_nxt = t;
+  }
+  next_w((size_t)D * Hd, w_hi, w_lo);                                     // :83
+  if ((rc = launch_gemm(o_hi, o_lo, w_hi, w_lo, rows, D, Hd, params[3 + 8 * blocks], nullptr, 0, raw, nullptr,
+                        nullptr, stream)))
+    return rc;
+  return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
+}

@@ -1,10 +1,12 @@
-"""DescriptorRefiner whose L2-normalising tail is a CUDA kernel.
+"""DescriptorRefiner running on the sm_100a kernels.
 
 Same surface and ``state_dict`` layout as the reference (models/descriptor_refiner.py:11-126
-there): ``input_proj``, ``residual_blocks.{i}.{norm1,fc1,norm2,fc2}``, ``output_proj``.  The MLP
-body runs on cuBLAS through PyTorch (SURVEY.md §8(f) N1 lists its fusion as the next step);
-``F.normalize`` is replaced by ``sslam_l2norm_rows``, which can also emit the bf16 copy the
-tensor-core matcher consumes.
+there): ``input_proj``, ``residual_blocks.{i}.{norm1,fc1,norm2,fc2}``, ``output_proj``.  Under
+``torch.no_grad()`` on a CUDA device the whole forward — six Linear layers as tcgen05 tf32x3 GEMMs
+with fused bias/ReLU/residual epilogues, LayerNorms, and the final ``F.normalize`` — is one call
+into ``sslam_refiner_forward_f32``.  When autograd is recording (training is
+out of scope) the PyTorch ops are used so gradients exist; ``mlp="torch"`` forces that path for
+A/B comparisons.
 """
 
 import torch
@@ -51,11 +53,40 @@ class DescriptorRefiner(nn.Module):
             x = blk(x)
         return self.output_proj(x)
 
+    mlp = "tcgen05"          # "tcgen05" (default) or "torch" (cuBLAS fp32 body + l2norm kernel)
+
+    def _ordered_params(self):
+        ps = [self.input_proj.weight, self.input_proj.bias]
+        for blk in self.residual_blocks:
+            ps += [blk.norm1.weight, blk.norm1.bias, blk.fc1.weight, blk.fc1.bias,
+                   blk.norm2.weight, blk.norm2.bias, blk.fc2.weight, blk.fc2.bias]
+        return ps + [self.output_proj.weight, self.output_proj.bias]
+
+    def _plan(self):
+        ps = self._ordered_params()
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_plan_key", None) != key:
+            for blk in self.residual_blocks:
+                if blk.norm1.eps != 1e-5 or blk.norm2.eps != 1e-5:
+                    raise RuntimeError("fused refiner assumes LayerNorm eps = 1e-5")
+            self._plan_obj = ops.RefinerPlan(ps, self.input_dim, self.input_proj.out_features,
+                                             self.output_dim, len(self.residual_blocks))
+            self._plan_key = key
+        return self._plan_obj
+
+    def forward_fused(self, dino_features: torch.Tensor, want_bf16: bool = False):
+        """(..., C) -> (rows, D) unit-norm fp32 [, bf16 copy] through sslam_refiner_forward_f32."""
+        return ops.refiner_forward(self._plan(), dino_features, want_bf16=want_bf16)
+
     def forward(self, dino_features: torch.Tensor) -> torch.Tensor:
         """(B, N, C) features at keypoints -> (B, N, output_dim) unit-norm descriptors."""
         B, N, _ = dino_features.shape
-        raw = self.forward_unnormalized(dino_features)
-        if raw.requires_grad:
-            # training needs autograd through the normalisation; the kernel has no backward
+        grad = torch.is_grad_enabled() and (dino_features.requires_grad or
+                                            any(p.requires_grad for p in self.parameters()))
+        if grad:
+            # training needs autograd; the kernels have no backward
+            raw = self.forward_unnormalized(dino_features)
             return F.normalize(raw, p=2, dim=-1).reshape(B, N, self.output_dim)
-        return ops.l2norm_rows(raw).reshape(B, N, self.output_dim)
+        if self.mlp == "torch":
+            return ops.l2norm_rows(self.forward_unnormalized(dino_features)).reshape(B, N, self.output_dim)
+        return self.forward_fused(dino_features).reshape(B, N, self.output_dim)

@@ -121,6 +121,45 @@ def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False):
     return (out, out_bf16) if want_bf16 else out
 
 
+class RefinerPlan:
+    """Device-side state for sslam_refiner_forward_f32: pointer table + packed tf32 hi/lo weights of
+    one DescriptorRefiner-shaped parameter set (state_dict order)."""
+
+    def __init__(self, tensors, C, Hd, D, blocks):
+        lib = _lib.load()
+        _need_cuda(*tensors)
+        self.tensors = [t.detach().contiguous() for t in tensors]
+        for t in self.tensors:
+            if t.dtype != torch.float32:
+                raise RuntimeError("refiner parameters must be fp32")
+        self.C, self.Hd, self.D, self.blocks = int(C), int(Hd), int(D), int(blocks)
+        assert len(self.tensors) == 4 + 8 * self.blocks
+        self.ptrs = (ctypes.c_void_p * len(self.tensors))(*[t.data_ptr() for t in self.tensors])
+        dev = self.tensors[0].device
+        nbytes = lib.sslam_refiner_packed_bytes(self.C, self.Hd, self.D, self.blocks)
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.sslam_refiner_pack_weights(self.ptrs, self.C, self.Hd, self.D, self.blocks,
+                                                  _ptr(self.packed), nbytes, _stream()))
+
+
+def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None):
+    """x (..., C) fp32 -> unit-norm descriptors (rows, D) fp32 [and bf16 copy]."""
+    lib = _lib.load()
+    _need_cuda(x)
+    xc = x.contiguous()
+    if xc.dtype != torch.float32 or xc.shape[-1] != plan.C:
+        raise RuntimeError("refiner_forward expects fp32 input with %d channels" % plan.C)
+    rows = xc.numel() // plan.C
+    out = torch.empty(rows, plan.D, dtype=torch.float32, device=xc.device)
+    out16 = torch.empty(rows, plan.D, dtype=torch.bfloat16, device=xc.device) if want_bf16 else None
+    need = lib.sslam_refiner_workspace_bytes(rows, plan.C, plan.Hd, plan.D, plan.blocks)
+    ws = workspace if workspace is not None else _ws("refiner", need, xc.device)
+    _lib.check(lib.sslam_refiner_forward_f32(plan.ptrs, _ptr(plan.packed), _ptr(xc), rows, plan.C,
+                                             plan.Hd, plan.D, plan.blocks, float(eps), _ptr(out),
+                                             _ptr(out16), _ptr(ws), ws.numel(), _stream()))
+    return (out, out16) if want_bf16 else out
+
+
 def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, workspace=None):
     """Row top-2 / column argmax of S_p = D1_p . D2_p^T without storing S.
 

@@ -42,15 +42,19 @@ class FrontEnd:
         self._mark(timers, "decode")
         sampled = ops.gather_bilinear(features, kp, pixel_coords=(self.grid == "pixel"))
         self._mark(timers, "gather")
-        raw = self.refiner.forward_unnormalized(sampled)
-        self._mark(timers, "refiner_mlp")
         B = kp.shape[0]
         res = dict(scores=sc, info=info)
-        if self.sim_mode == SIM_BF16:
-            d32, d16 = ops.l2norm_rows(raw, want_bf16=True)
-            res["descriptors_bf16"] = d16.reshape(B, self.K, -1)
+        want16 = self.sim_mode == SIM_BF16
+        if getattr(self.refiner, "mlp", "torch") == "tcgen05":
+            out = self.refiner.forward_fused(sampled, want_bf16=want16)      # MLP + L2 norm, one call
+            self._mark(timers, "refiner_mlp")
         else:
-            d32 = ops.l2norm_rows(raw)
+            raw = self.refiner.forward_unnormalized(sampled)
+            self._mark(timers, "refiner_mlp")
+            out = ops.l2norm_rows(raw, want_bf16=want16)
+        d32, d16 = out if want16 else (out, None)
+        if want16:
+            res["descriptors_bf16"] = d16.reshape(B, self.K, -1)
         self._mark(timers, "l2norm")
         res["descriptors"] = d32.reshape(B, self.K, -1)
         res["keypoints_pixel"] = kp if self.grid == "pixel" else kp * self.patch + self.patch / 2

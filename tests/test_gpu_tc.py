@@ -154,3 +154,36 @@ def test_bf16_sequence_scores(dev):
     print(f"bf16 K=4096: index agreement {100 * agree:.2f}% of {len(ref)} matches, max rel score err {rel:.2e}")
     assert agree > 0.98
     assert rel < 1e-2
+
+
+def test_refiner_fused_vs_oracle_and_torch(dev):
+    """DescriptorRefiner on tcgen05 (tf32x3 GEMMs + fused epilogues): descriptors within 1e-5 abs of
+    the fp32 oracle (north_star / SURVEY.md §8(d)) and of the cuBLAS-fp32 PyTorch body."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from parity import load_golden
+    torch.manual_seed(0)
+    for (C, Hd, D, layers, rows) in ((384, 384, 256, 4, 2048 + 77), (384, 384, 128, 4, 500), (64, 96, 32, 2, 130),
+                                     (48, 64, 32, 5, 40)):
+        m = DescriptorRefiner(C, Hd, D, layers).to(dev).eval()
+        g = torch.Generator().manual_seed(rows)
+        x = torch.randn(1, rows, C, generator=g).to(dev)
+        with torch.no_grad():
+            fused = m(x)
+            m.mlp = "torch"
+            ref_t = m(x)
+            m.mlp = "tcgen05"
+        w = oracle.RefinerWeights.from_state_dict(m.state_dict())
+        ref_o = oracle.refiner_forward(w, x.cpu().numpy())
+        err_o = np.abs(fused.cpu().numpy() - ref_o).max()
+        err_t = (fused - ref_t).abs().max().item()
+        print(f"refiner {C}-{Hd}-{D} x{layers} rows={rows}: max|fused-oracle| {err_o:.2e}  max|fused-torch| {err_t:.2e}")
+        assert err_o < 1e-5 and err_t < 1e-5
+        assert torch.allclose(fused.norm(dim=-1), torch.ones_like(fused[..., 0]), atol=1e-5)
+    # golden weights written by the reference's own module
+    z, _ = load_golden("refiner")
+    m = DescriptorRefiner(input_dim=48, hidden_dim=64, output_dim=32, num_layers=4)
+    m.load_state_dict({k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")})
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        out = m(cu(z["x"], dev)).cpu().numpy()
+    assert np.abs(out - z["out"]).max() < 1e-5
