@@ -6,7 +6,9 @@
 
 Workload (BASELINE.json configs[1], "c2"): a TUM-RGB-D-shaped synthetic sequence of 600 frames,
 640x480 saliency maps + 30x40x384 NHWC feature maps already past the backbone, K = 2048 keypoints,
-D = 256, consecutive-pair matching with matcher M1 (ratio 0.8), fp32 exact mode.  One *step* is one
+D = 256, consecutive-pair matching with matcher M1 (ratio 0.8), fp32 mode (descriptors fp32; the
+similarity and the refiner GEMMs run as 3-term TF32 splits on tcgen05, error < 3e-6 — `--mode f32`
+selects the CUDA-core exact kernel, `--mode bf16` the bf16 similarity of config c3).  One *step* is one
 pass over the whole sequence: every frame is extracted once (decode -> sample -> refiner MLP ->
 L2 norm) and each of the 599 consecutive pairs is matched.  With N GPUs every rank processes its
 own 600-frame sequence (weak scaling) and the match lists are gathered on rank 0 over NCCL.
@@ -182,7 +184,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     mode_name = a.mode
     if mode_name == "auto":
-        mode_name = os.environ.get("SSLAM_BENCH_MODE", "f32")
+        # "fp32 mode" of BASELINE config c2: fp32 in/out, 3-term TF32 split on the tensor cores
+        mode_name = os.environ.get("SSLAM_BENCH_MODE", "tf32x3")
     mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16}[mode_name]
 
     torch.manual_seed(0)
