@@ -78,6 +78,15 @@ int sslam_device_check(void);
 /* Number of kernel launches (not memsets) this process enqueued through the library so far. */
 uint64_t sslam_launch_count(void);
 
+/* Optional per-kernel timing for benchmarks: while enabled, every kernel launch of the library is
+ * bracketed by CUDA events on its launch stream.  sslam_profile_enable() also clears the records;
+ * sslam_profile_read() waits for the recorded events of one kernel kind (0 .. kinds-1) and returns
+ * their summed duration and count.  Off by default (no events, no overhead). */
+int sslam_profile_enable(int on);
+int sslam_profile_kinds(void);
+const char* sslam_profile_kind_name(int kind);
+int sslam_profile_read(int kind, double* total_ms, uint64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------
  * Heatmap decode.  Replaces KeypointSelector.select_keypoints / _apply_nms and, with
  * from_logits != 0, the sigmoid tail of KeypointSelector.forward

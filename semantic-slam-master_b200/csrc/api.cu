@@ -2,6 +2,7 @@
 #include <stdarg.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -15,6 +16,33 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// ---- optional per-kernel timing: CUDA events recorded around every launch on the launch stream
+std::atomic<int> g_profile_on{0};
+namespace {
+struct ProfRec { int kind; cudaEvent_t beg, end; };
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+}  // namespace
+
+void prof_mark(int kind, cudaStream_t stream, bool begin) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (begin) {
+    ProfRec r{kind, prof_event(), nullptr};
+    cudaEventRecord(r.beg, stream);
+    g_prof_recs.push_back(r);
+  } else if (!g_prof_recs.empty() && g_prof_recs.back().end == nullptr) {
+    g_prof_recs.back().end = prof_event();
+    cudaEventRecord(g_prof_recs.back().end, stream);
+  }
 }
 
 static int query_device(int* sms) {
@@ -68,3 +96,41 @@ extern "C" int sslam_last_error(char* buf, size_t len) {
 extern "C" int sslam_device_check(void) { return sslam::check_device(); }
 
 extern "C" uint64_t sslam_launch_count(void) { return sslam::g_launches.load(); }
+
+static const char* const kKindNames[sslam::KK_COUNT] = {
+    "decode_scan", "decode_topk", "decode_count", "decode_resolve", "nms", "gather", "l2norm",
+    "match_f32", "match_tc", "split_tf32", "unpack_cols", "match_finalize", "gemm_tf32x3", "layernorm_split"};
+
+extern "C" int sslam_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(sslam::g_prof_mu);
+  for (auto& r : sslam::g_prof_recs) {
+    if (r.beg) sslam::g_prof_pool.push_back(r.beg);
+    if (r.end) sslam::g_prof_pool.push_back(r.end);
+  }
+  sslam::g_prof_recs.clear();
+  sslam::g_profile_on.store(on ? 1 : 0);
+  return SSLAM_OK;
+}
+
+extern "C" int sslam_profile_kinds(void) { return sslam::KK_COUNT; }
+
+extern "C" const char* sslam_profile_kind_name(int kind) {
+  return (kind >= 0 && kind < sslam::KK_COUNT) ? kKindNames[kind] : "";
+}
+
+extern "C" int sslam_profile_read(int kind, double* total_ms, uint64_t* launches) {
+  std::lock_guard<std::mutex> lk(sslam::g_prof_mu);
+  double ms = 0.0;
+  uint64_t n = 0;
+  for (auto& r : sslam::g_prof_recs) {
+    if (r.kind != kind || !r.end) continue;
+    SSLAM_CHECK_CUDA(cudaEventSynchronize(r.end));
+    float t = 0.f;
+    SSLAM_CHECK_CUDA(cudaEventElapsedTime(&t, r.beg, r.end));
+    ms += t;
+    ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  return SSLAM_OK;
+}

@@ -39,9 +39,22 @@ extern std::atomic<uint64_t> g_launches;
     }                                                                                 \
   } while (0)
 
-// call right after a <<<>>> launch
-#define SSLAM_LAUNCHED()                                                              \
+// kernel kinds for the launch counter / optional per-kernel event timing (sslam_profile_*)
+enum KernelKind {
+  KK_DECODE_SCAN = 0, KK_DECODE_TOPK, KK_DECODE_COUNT, KK_DECODE_RESOLVE, KK_NMS, KK_GATHER, KK_L2NORM,
+  KK_MATCH_F32, KK_MATCH_TC, KK_SPLIT, KK_UNPACK, KK_FINALIZE, KK_GEMM, KK_LAYERNORM, KK_COUNT
+};
+extern std::atomic<int> g_profile_on;
+void prof_mark(int kind, cudaStream_t stream, bool begin);
+
+// SSLAM_LAUNCH(kind, stream, kernel<<<grid, block, smem, stream>>>(args...));
+#define SSLAM_LAUNCH(kind, stream, ...)                                               \
   do {                                                                                \
+    if (::sslam::g_profile_on.load(std::memory_order_relaxed))                        \
+      ::sslam::prof_mark(kind, stream, true);                                         \
+    __VA_ARGS__;                                                                      \
+    if (::sslam::g_profile_on.load(std::memory_order_relaxed))                        \
+      ::sslam::prof_mark(kind, stream, false);                                        \
     ::sslam::g_launches.fetch_add(1, std::memory_order_relaxed);                      \
     SSLAM_CHECK_CUDA(cudaGetLastError());                                             \
   } while (0)

@@ -445,8 +445,8 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
   const int r = nms_radius;
   size_t scan_smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
   dim3 g1((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
-  decode_scan_kernel<<<g1, SCAN_THREADS, scan_smem, stream>>>(p);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
+               decode_scan_kernel<<<g1, SCAN_THREADS, scan_smem, stream>>>(p));
 
   const int kpad = next_pow2(K);
   size_t sel_smem = (size_t)kpad * 8 + sizeof(SelectScratch);
@@ -458,16 +458,15 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured.store(160 * 1024);
   }
-  decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_DECODE_TOPK, stream,
+               decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));
 
   int chunks = (H * W + 16383) / 16384;
   if (chunks < 1) chunks = 1;
-  decode_count_kernel<<<B * chunks, 256, 0, stream>>>(p, chunks);
-  SSLAM_LAUNCHED();
-
-  decode_resolve_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_DECODE_COUNT, stream,
+               decode_count_kernel<<<B * chunks, 256, 0, stream>>>(p, chunks));
+  SSLAM_LAUNCH(KK_DECODE_RESOLVE, stream,
+               decode_resolve_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));
   return SSLAM_OK;
 }
 
@@ -489,7 +488,7 @@ extern "C" int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radi
   const int r = nms_radius;
   size_t smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
   dim3 g((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
-  nms_kernel<<<g, SCAN_THREADS, smem, stream>>>(sal, H, W, r, out);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_NMS, stream,
+               nms_kernel<<<g, SCAN_THREADS, smem, stream>>>(sal, H, W, r, out));
   return SSLAM_OK;
 }

@@ -159,13 +159,13 @@ extern "C" int sslam_gather_bilinear_f32(const float* feat, const float* kpts, i
   const unsigned blocks = (unsigned)((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  if (vec)
-    gather_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
-                                                                    coords, out);
-  else
-    gather_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
-                                                                     coords, out);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_GATHER, stream,
+               if (vec)
+      gather_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
+                                                                      coords, out);
+    else
+      gather_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
+                                                                       coords, out));
   return SSLAM_OK;
 }
 
@@ -181,12 +181,12 @@ extern "C" int sslam_l2norm_rows(const float* in, int rows, int D, float eps, fl
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                    (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) &&
                    (!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0);
-  if (vec)
-    l2norm_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
-        in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
-  else
-    l2norm_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
-        in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_L2NORM, stream,
+               if (vec)
+      l2norm_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
+          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+    else
+      l2norm_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
+          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16)));
   return SSLAM_OK;
 }

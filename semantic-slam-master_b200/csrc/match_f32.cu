@@ -355,16 +355,16 @@ extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, in
       configured.store(true);
     }
     dim3 grid((N + BM - 1) / BM, P);
-    match_f32_kernel<<<grid, THREADS, smem, stream>>>(mp);
-    SSLAM_LAUNCHED();
+    SSLAM_LAUNCH(KK_MATCH_F32, stream,
+                 match_f32_kernel<<<grid, THREADS, smem, stream>>>(mp));
   } else {
     rc = match_top2_tc(bank1, F1, bank2, F2, pair_index, dtype, P, N, M, D, nn12, best12, second12, colkeys,
                        reinterpret_cast<char*>(ws) + colbytes, ws_bytes - colbytes, stream);
     if (rc) return rc;
   }
   const long long total = (long long)P * M;
-  unpack_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(colkeys, total, nn21, best21);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_UNPACK, stream,
+               unpack_cols_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(colkeys, total, nn21, best21));
   return SSLAM_OK;
 }
 
@@ -392,7 +392,7 @@ extern "C" int sslam_match_finalize(int variant, const float* params, const int3
   f.nn12 = nn12; f.best12 = best12; f.second12 = second12; f.nn21 = nn21; f.best21 = best21;
   f.scores1 = scores1; f.scores2 = scores2; f.inten1 = inten1; f.inten2 = inten2;
   f.pairs = pairs; f.pair_scores = pair_scores; f.counts = counts;
-  finalize_kernel<<<P, 256, 0, stream>>>(f);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_FINALIZE, stream,
+               finalize_kernel<<<P, 256, 0, stream>>>(f));
   return SSLAM_OK;
 }

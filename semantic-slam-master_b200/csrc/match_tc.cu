@@ -365,8 +365,8 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
     configured.store(true);
   }
   const int strips = (tp.N + BM - 1) / BM;
-  match_tc_kernel<MODE><<<strips * tp.P, NUM_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_MATCH_TC, stream,
+               match_tc_kernel<MODE><<<strips * tp.P, NUM_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp));
   return SSLAM_OK;
 }
 
@@ -396,9 +396,9 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
   float* h1 = reinterpret_cast<float*>(w);
   float* l1 = reinterpret_cast<float*>(w + align_up(n1 * 4, 256));
   const int sms = num_sms();
-  split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f1),
-                                                 reinterpret_cast<float4*>(h1), reinterpret_cast<float4*>(l1), n1 / 4);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_SPLIT, stream,
+               split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f1),
+                                                   reinterpret_cast<float4*>(h1), reinterpret_cast<float4*>(l1), n1 / 4));
   float *h2, *l2;
   uint64_t rows2;
   if (pl.shared) {
@@ -410,9 +410,9 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
     char* w2 = w + 2 * align_up(n1 * 4, 256);
     h2 = reinterpret_cast<float*>(w2);
     l2 = reinterpret_cast<float*>(w2 + align_up(n2 * 4, 256));
-    split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f2),
-                                                   reinterpret_cast<float4*>(h2), reinterpret_cast<float4*>(l2), n2 / 4);
-    SSLAM_LAUNCHED();
+    SSLAM_LAUNCH(KK_SPLIT, stream,
+                 split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f2),
+                                                     reinterpret_cast<float4*>(h2), reinterpret_cast<float4*>(l2), n2 / 4));
     rows2 = (uint64_t)F2 * M;
   }
   if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;

@@ -265,9 +265,9 @@ layernorm_split_kernel(const float* __restrict__ x, int rows, int W, const float
 }
 
 int launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t stream) {
-  split_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                                  reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n / 4);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_SPLIT, stream,
+               split_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                    reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n / 4));
   return SSLAM_OK;
 }
 
@@ -289,18 +289,18 @@ int launch_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const f
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
   gp.out_f32 = out_f32; gp.out_hi = out_hi; gp.out_lo = out_lo;
-  gemm_tf32x3_kernel<<<(rows + BM - 1) / BM, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_GEMM, stream,
+               gemm_tf32x3_kernel<<<(rows + BM - 1) / BM, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
   return SSLAM_OK;
 }
 
 int launch_layernorm(const float* x, int rows, int W, const float* g, const float* b, float* hi, float* lo,
                      cudaStream_t stream) {
   const unsigned blocks = (unsigned)((rows + 7) / 8);
-  if (W <= 128) layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
-  else if (W <= 384) layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
-  else layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
-  SSLAM_LAUNCHED();
+  SSLAM_LAUNCH(KK_LAYERNORM, stream,
+               if (W <= 128) layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
+    else if (W <= 384) layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
+    else layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo));
   return SSLAM_OK;
 }
 

@@ -14,6 +14,10 @@ SIGNATURES = {
     "sslam_last_error": (c_int, [ctypes.c_char_p, c_size_t]),
     "sslam_device_check": (c_int, []),
     "sslam_launch_count": (ctypes.c_uint64, []),
+    "sslam_profile_enable": (c_int, [c_int]),
+    "sslam_profile_kinds": (c_int, []),
+    "sslam_profile_kind_name": (ctypes.c_char_p, [c_int]),
+    "sslam_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "sslam_decode_workspace_bytes": (c_size_t, [c_int] * 4),
     "sslam_decode_topk_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float,
                                       c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

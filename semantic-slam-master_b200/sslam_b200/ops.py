@@ -29,6 +29,23 @@ def launch_count():
     return int(_lib.load().sslam_launch_count())
 
 
+def profile_enable(on=True):
+    """Bracket every library kernel launch with CUDA events (benchmarks only)."""
+    _lib.check(_lib.load().sslam_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{kernel kind: (total ms, launches)} for the launches recorded since profile_enable()."""
+    lib = _lib.load()
+    out = {}
+    for k in range(lib.sslam_profile_kinds()):
+        ms, n = ctypes.c_double(0), ctypes.c_uint64(0)
+        _lib.check(lib.sslam_profile_read(k, ctypes.byref(ms), ctypes.byref(n)))
+        if n.value:
+            out[lib.sslam_profile_kind_name(k).decode()] = (ms.value, int(n.value))
+    return out
+
+
 class Workspace:
     """Grow-only device scratch buffer (one per stream of use)."""
 
