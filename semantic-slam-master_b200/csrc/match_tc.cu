@@ -14,7 +14,8 @@
 //                      decisions are identical except for similarity near-ties (< 1e-6), which the
 //                      parity tests count.
 //
-// CTA = one 128-row strip of one pair; it walks the column tiles (128 wide) of the pair:
+// Persistent kernel, one CTA per SM.  A work item is one 128-row strip of one pair (items blockIdx,
+// +gridDim, ...); inside an item the CTA walks the column tiles (128 wide) of the pair:
 //   warp 0      TMA producer   : per k-block (128 bytes of K) loads the A and B tiles of every term
 //   warp 1      MMA issuer     : one elected thread issues tcgen05.mma; tcgen05.commit releases the
 //                                smem stage and, after the last k-block, publishes the accumulator
@@ -94,13 +95,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int strips = (p.N + BM - 1) / BM;
-  const int pair = blockIdx.x / strips;
-  const int strip = blockIdx.x - pair * strips;
-  int ia = pair, ib = pair;
-  if (p.pair_index) { ia = p.pair_index[2 * pair]; ib = p.pair_index[2 * pair + 1]; }
-  const int row0 = strip * BM;
-  const int a_row = ia * p.N + row0;           // row coordinate in the [F*N, D] tensor map
-  const int b_row0 = ib * p.M;
+  const int nitems = strips * p.P;             // persistent: items blockIdx.x, +gridDim.x, ...
   const int ntile = (p.M + BN - 1) / BN;
   const int nkb = (p.D + C::BK - 1) / C::BK;
 
@@ -121,6 +116,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
       prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmB_hi);
       if (C::TERMS == 2) { prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_lo); }
       int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const int pair = item / strips;
+      int ia = pair, ib = pair;
+      if (p.pair_index) { ia = p.pair_index[2 * pair]; ib = p.pair_index[2 * pair + 1]; }
+      const int a_row = ia * p.N + (item - pair * strips) * BM;   // row coordinate in the [F*N, D] map
+      const int b_row0 = ib * p.M;
       for (int ct = 0; ct < ntile; ++ct) {
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -135,15 +136,17 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
       const uint32_t idesc = make_instr_desc(C::TF32 ? FMT_TF32 : FMT_BF16, BM, BN);
       int stage = 0; uint32_t phase = 0;
-      for (int ct = 0; ct < ntile; ++ct) {
-        const int acc = ct & 1;
-        const uint32_t acc_phase = (ct >> 1) & 1;
+      const int my_tiles = ((nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile;
+      for (int tc = 0; tc < my_tiles; ++tc) {                   // tc: running tile count of this CTA
+        const int acc = tc & 1;
+        const uint32_t acc_phase = (tc >> 1) & 1;
         mbar_wait(&tempty[acc], acc_phase ^ 1);                 // epilogue drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;          // Ah.Bh (or the only term)
@@ -179,17 +182,21 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     const int q = warp & 3;                                     // TMEM lane quarter of this warp
     const int ew = warp - 2;                                    // 0..3, slot in colpart
     const int et = threadIdx.x - 64;                            // 0..127
-    const int grow = row0 + q * 32 + lane;                      // global row of this thread
-    const bool row_ok = grow < p.N;
     float* tp = transp + ew * 32 * TP_LD;
+    const float NEG_INF = __int_as_float(0xff800000);
+    int tc = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int pair = item / strips;
+    const int row0 = (item - pair * strips) * BM;
+    const int grow = row0 + q * 32 + lane;                      // row of this thread inside the pair
+    const bool row_ok = grow < p.N;
     int nvalid = p.N - (row0 + q * 32);                         // valid rows of this warp (uniform)
     nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
-    const float NEG_INF = __int_as_float(0xff800000);
     float best = NEG_INF, second = NEG_INF;
     int bidx = 0x7fffffff;
-    for (int ct = 0; ct < ntile; ++ct) {
-      const int acc = ct & 1;
-      const uint32_t acc_phase = (ct >> 1) & 1;
+    for (int ct = 0; ct < ntile; ++ct, ++tc) {
+      const int acc = tc & 1;
+      const uint32_t acc_phase = (tc >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tcgen05_fence_after();
       u64* cp = colpart + (acc * 4 + ew) * BN;
@@ -268,6 +275,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     if (row_ok) {
       const size_t o = (size_t)pair * p.N + grow;
       p.nn12[o] = bidx; p.best12[o] = best; p.second12[o] = second;
+    }
     }
   }
   tcgen05_fence_before();

@@ -13,7 +13,9 @@
 //     global stores are 128-byte coalesced.
 //   * LayerNorm is a warp-per-row kernel that reads fp32 and writes the (hi, lo) pair.
 //
-// One CTA = a 128-row strip; it walks the N/128 column tiles of the layer.  Activations round-trip
+// Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
+// inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
+// store epilogue of a strip overlaps the MMAs of the next.  Activations round-trip
 // HBM between layers (rows x 384 fp32); the whole chain is ~10 launches per call.
 #include "tc_common.cuh"
 
@@ -61,7 +63,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = blockIdx.x * BM;
+  const int nstrips = (p.rows + BM - 1) / BM;       // persistent: strips blockIdx.x, +gridDim.x, ...
   const int ntile = (p.N + BN - 1) / BN;
   const int nkb = (p.K + BK - 1) / BK;
 
@@ -81,17 +83,20 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
       prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
       int stage = 0; uint32_t phase = 0;
-      for (int ct = 0; ct < ntile; ++ct) {
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* st = operands + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          const int kc = kb * BK;
-          tma_load_2d(st, &tmA_hi, &full[stage], kc, row0);
-          tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, row0);
-          tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, ct * BN);
-          tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, ct * BN);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+        const int row0 = strip * BM;
+        for (int ct = 0; ct < ntile; ++ct) {
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* st = operands + stage * STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            const int kc = kb * BK;
+            tma_load_2d(st, &tmA_hi, &full[stage], kc, row0);
+            tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, row0);
+            tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, ct * BN);
+            tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, ct * BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -99,9 +104,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     if (elect_one()) {                                            // ---- MMA issuer
       const uint32_t idesc = make_instr_desc(FMT_TF32, BM, BN);
       int stage = 0; uint32_t phase = 0;
-      for (int ct = 0; ct < ntile; ++ct) {
-        const int acc = ct & 1;
-        mbar_wait(&tempty[acc], ((ct >> 1) & 1) ^ 1);
+      const int my_tiles = ((nstrips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile;
+      for (int tc = 0; tc < my_tiles; ++tc) {           // tc: running tile count of this CTA
+        const int acc = tc & 1;
+        mbar_wait(&tempty[acc], ((tc >> 1) & 1) ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 2 * BN;
         const uint32_t tmem_s = tmem_d + BN;
@@ -132,12 +138,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
     const int q = warp & 3;
     const int ew = warp - 2;
     float* tp = transp + ew * 32 * TP_LD;
-    const int wrow0 = row0 + q * 32;                    // first global row of this warp
     const int sub_r = lane >> 3;                        // store mapping: 8 lanes per row, 4 rows per pass
     const int sub_c = (lane & 7) * 4;
-    for (int ct = 0; ct < ntile; ++ct) {
-      const int acc = ct & 1;
-      mbar_wait(&tfull[acc], (ct >> 1) & 1);
+    int tc = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
+    for (int ct = 0; ct < ntile; ++ct, ++tc) {
+      const int wrow0 = strip * BM + q * 32;            // first global row of this warp
+      const int acc = tc & 1;
+      mbar_wait(&tfull[acc], (tc >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
@@ -290,7 +298,9 @@ int launch_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const f
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
   gp.out_f32 = out_f32; gp.out_hi = out_hi; gp.out_lo = out_lo;
   SSLAM_LAUNCH(KK_GEMM, stream,
-               gemm_tf32x3_kernel<<<(rows + BM - 1) / BM, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
+               const int strips = (rows + BM - 1) / BM;
+  const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
+  gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
   return SSLAM_OK;
 }
 
