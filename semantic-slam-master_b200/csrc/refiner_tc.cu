@@ -29,11 +29,12 @@ constexpr int BM = 128, BN = 128, BK = 32;               // BK fp32 = 128 bytes 
 constexpr int BLOCK_BYTES = BM * 128;
 constexpr int STAGES = 3;
 constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A_hi, A_lo, B_hi, B_lo
-constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 cross)
-constexpr int TP_LD = 36;
+constexpr int TP_LD = 20;                                // 16 columns + 4 pad (floats)
 constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
-constexpr int SMEM_TRANSP = 4 * 32 * TP_LD * 4;
+constexpr int SMEM_TRANSP = EPI_WARPS * 32 * TP_LD * 4;
 constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
 constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_BARS + 1024;
 
@@ -69,7 +70,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -134,12 +135,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       }
     }
   } else {
-    // ---- epilogue warps 2..5: TMEM -> (+bias, +residual, relu) -> smem transpose -> coalesced stores
+    // ---- epilogue warps 2..9: TMEM -> smem transpose -> (+bias, +residual, relu) -> coalesced stores.
+    // Warps w and w+4 share a TMEM lane quarter and each take half of the tile's 128 columns, in
+    // units of 16 columns.
     const int q = warp & 3;
     const int ew = warp - 2;
+    const int half = ew >> 2;                           // which 64 columns of the tile
     float* tp = transp + ew * 32 * TP_LD;
-    const int sub_r = lane >> 3;                        // store mapping: 8 lanes per row, 4 rows per pass
-    const int sub_c = (lane & 7) * 4;
+    const int sub_r = lane >> 2;                        // store mapping: 4 lanes per row, 8 rows per pass
+    const int sub_c = (lane & 3) * 4;
     int tc = 0;
     for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
     for (int ct = 0; ct < ntile; ++ct, ++tc) {
@@ -148,15 +152,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
       mbar_wait(&tfull[acc], (tc >> 1) & 1);
       tcgen05_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32], rs[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + ch * 32;
-        tmem_ld_32x32(taddr, r);
-        tmem_ld_32x32(taddr + BN, rs);
+      for (int un = 0; un < 4; ++un) {
+        const int col0 = half * 64 + un * 16;           // first column of this unit inside the tile
+        uint32_t r[16], rs[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0;
+        tmem_ld_32x16(taddr, r);
+        tmem_ld_32x16(taddr + BN, rs);
         tmem_ld_wait();
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           float4 v;
           v.x = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rs[j]));
           v.y = __fadd_rn(__uint_as_float(r[j + 1]), __uint_as_float(rs[j + 1]));
@@ -165,12 +170,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
         }
         __syncwarp();
-        const int gc = ct * BN + ch * 32 + sub_c;       // first of this lane's 4 columns
+        const int gc = ct * BN + col0 + sub_c;          // first of this lane's 4 columns
         if (gc < p.N) {                                 // N % 4 == 0
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
+          float4 res[4];
+          if (p.residual) {
 #pragma unroll
-          for (int pass = 0; pass < 8; ++pass) {
-            const int lr = pass * 4 + sub_r;
+            for (int pass = 0; pass < 4; ++pass) {
+              const int gr = wrow0 + pass * 8 + sub_r;
+              res[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)gr * p.N + gc))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int pass = 0; pass < 4; ++pass) {
+            const int lr = pass * 8 + sub_r;
             const int gr = wrow0 + lr;
             if (gr < p.rows) {
               float4 v = *reinterpret_cast<const float4*>(tp + lr * TP_LD + sub_c);
@@ -178,9 +192,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
               const size_t o = (size_t)gr * p.N + gc;
               if (p.residual) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(p.residual + o));
-                v.x = __fadd_rn(v.x, rr.x); v.y = __fadd_rn(v.y, rr.y);
-                v.z = __fadd_rn(v.z, rr.z); v.w = __fadd_rn(v.w, rr.w);
+                v.x = __fadd_rn(v.x, res[pass].x); v.y = __fadd_rn(v.y, res[pass].y);
+                v.z = __fadd_rn(v.z, res[pass].z); v.w = __fadd_rn(v.w, res[pass].w);
               }
               if (p.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
