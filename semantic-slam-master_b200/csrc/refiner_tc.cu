@@ -8,10 +8,13 @@
 //     (x = hi + lo, both round-to-nearest tf32;  x.w ~= hi.hi' + hi.lo' + lo.hi'), operands fed by
 //     TMA into 128B-swizzled smem, accumulators in TMEM.  As in match_tc.cu the small cross terms
 //     get their own accumulator so that the tensor core's truncating accumulate does not eat them.
+//   * activations stay plain fp32 in HBM: the A tile is TMA-loaded raw and four converter warps
+//     split it in shared memory (hi in place, lo next to it, same swizzled offsets) before the MMA
+//     warp consumes it, so no (hi, lo) copies of activations ever touch HBM; weights are split
+//     once by sslam_refiner_pack_weights.
 //   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes
-//     either fp32 or the (hi, lo) pair the next GEMM consumes, through a smem transpose so that
-//     global stores are 128-byte coalesced.
-//   * LayerNorm is a warp-per-row kernel that reads fp32 and writes the (hi, lo) pair.
+//     fp32 through a smem transpose so that global stores are coalesced.
+//   * LayerNorm is a warp-per-row fp32 kernel.
 //
 // Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
 // inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
@@ -28,14 +31,16 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 32;               // BK fp32 = 128 bytes of K
 constexpr int BLOCK_BYTES = BM * 128;
 constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A_hi, A_lo, B_hi, B_lo
+constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A (raw -> hi), A_lo, B_hi, B_lo
+constexpr int TMA_BYTES = 3 * BLOCK_BYTES;               // A raw, B_hi, B_lo arrive by TMA
 constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int CONV_WARPS = 4;                            // fp32 -> (tf32 hi, tf32 lo) split of the A tile
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * CONV_WARPS;
 constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 cross)
 constexpr int TP_LD = 20;                                // 16 columns + 4 pad (floats)
 constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
 constexpr int SMEM_TRANSP = EPI_WARPS * 32 * TP_LD * 4;
-constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_BARS = (3 * STAGES + 4) * 8 + 16;
 constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_BARS + 1024;
 
 struct GemmParams {
@@ -43,15 +48,12 @@ struct GemmParams {
   const float* bias;        // [N]
   const float* residual;    // [rows, N] or null
   int relu;
-  float* out_f32;           // [rows, N] or null
-  float* out_hi;            // [rows, N] or null (with out_lo)
-  float* out_lo;
+  float* out_f32;           // [rows, N]
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                   GemmParams p) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
+                   const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* operands = smem;
@@ -59,7 +61,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* conv = bars + 2 * STAGES;                    // A tile split and visible to the async proxy
+  uint64_t* tfull = bars + 3 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -69,7 +72,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
   const int nkb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], CONV_WARPS);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -81,8 +86,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
 
   if (warp == 0) {
     if (elect_one()) {                                            // ---- TMA producer
-      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
-      prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+      prefetch_tensormap(&tmA); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
       int stage = 0; uint32_t phase = 0;
       for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int row0 = strip * BM;
@@ -90,10 +94,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* st = operands + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            mbar_arrive_expect_tx(&full[stage], TMA_BYTES);
             const int kc = kb * BK;
-            tma_load_2d(st, &tmA_hi, &full[stage], kc, row0);
-            tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, row0);
+            tma_load_2d(st, &tmA, &full[stage], kc, row0);
             tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, ct * BN);
             tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, ct * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -113,7 +116,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
         const uint32_t tmem_d = tmem_base + acc * 2 * BN;
         const uint32_t tmem_s = tmem_d + BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&conv[stage], phase);               // TMA landed and the A tile has been split
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(operands + stage * STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc_sw128(sa);
@@ -133,6 +136,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+    }
+  } else if (warp >= 2 + EPI_WARPS) {
+    // ---- converter warps: A tile fp32 -> tf32 hi (in place) + tf32 lo, element for element at the
+    // same (swizzled) offsets, then publish to the async proxy that tcgen05.mma reads through
+    const int cid = (warp - (2 + EPI_WARPS)) * 32 + lane;
+    int stage = 0; uint32_t phase = 0;
+    const int my_kblocks = ((nstrips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile * nkb;
+    for (int it = 0; it < my_kblocks; ++it) {
+      mbar_wait(&full[stage], phase);
+      float4* a = reinterpret_cast<float4*>(operands + stage * STAGE_BYTES);
+      float4* alo = a + BLOCK_BYTES / 16;
+#pragma unroll
+      for (int i = 0; i < BLOCK_BYTES / 16 / (32 * CONV_WARPS); ++i) {
+        const int e = cid + i * 32 * CONV_WARPS;
+        const float4 x = a[e];
+        float4 h, l;
+        h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+        l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
+        l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
+        a[e] = h; alo[e] = l;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[stage]);
+      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     // ---- epilogue warps 2..9: TMEM -> smem transpose -> (+bias, +residual, relu) -> coalesced stores.
@@ -198,15 +226,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_cons
               if (p.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
-              if (p.out_hi) {
-                float4 h, l;
-                h.x = to_tf32_rna(v.x); h.y = to_tf32_rna(v.y); h.z = to_tf32_rna(v.z); h.w = to_tf32_rna(v.w);
-                l.x = to_tf32_rna(__fsub_rn(v.x, h.x)); l.y = to_tf32_rna(__fsub_rn(v.y, h.y));
-                l.z = to_tf32_rna(__fsub_rn(v.z, h.z)); l.w = to_tf32_rna(__fsub_rn(v.w, h.w));
-                *reinterpret_cast<float4*>(p.out_hi + o) = h;
-                *reinterpret_cast<float4*>(p.out_lo + o) = l;
-              }
+              *reinterpret_cast<float4*>(p.out_f32 + o) = v;
             }
           }
         }
@@ -236,12 +256,11 @@ __global__ void split_kernel(const float4* __restrict__ src, float4* __restrict_
 }
 
 // LayerNorm over the last dim (torch.nn.LayerNorm, eps inside the sqrt, biased variance), one warp
-// per row, row held in registers (W <= 1024); writes the tf32 hi/lo pair for the next GEMM.
+// per row, row held in registers (W <= 1024).
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-layernorm_split_kernel(const float* __restrict__ x, int rows, int W, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, float* __restrict__ hi,
-                       float* __restrict__ lo) {
+layernorm_kernel(const float* __restrict__ x, int rows, int W, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -273,14 +292,10 @@ layernorm_split_kernel(const float* __restrict__ x, int rows, int W, const float
     if (c < W) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
       const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      float4 y, h, l;
+      float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
       y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      h.x = to_tf32_rna(y.x); h.y = to_tf32_rna(y.y); h.z = to_tf32_rna(y.z); h.w = to_tf32_rna(y.w);
-      l.x = to_tf32_rna(__fsub_rn(y.x, h.x)); l.y = to_tf32_rna(__fsub_rn(y.y, h.y));
-      l.z = to_tf32_rna(__fsub_rn(y.z, h.z)); l.w = to_tf32_rna(__fsub_rn(y.w, h.w));
-      *reinterpret_cast<float4*>(hi + (size_t)row * W + c) = h;
-      *reinterpret_cast<float4*>(lo + (size_t)row * W + c) = l;
+      *reinterpret_cast<float4*>(out + (size_t)row * W + c) = y;
     }
   }
 }
@@ -292,13 +307,11 @@ int launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t 
   return SSLAM_OK;
 }
 
-int launch_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const float* w_lo, int rows, int N,
-                int K, const float* bias, const float* residual, int relu, float* out_f32, float* out_hi,
-                float* out_lo, cudaStream_t stream) {
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+int launch_gemm(const float* a, const float* w_hi, const float* w_lo, int rows, int N, int K,
+                const float* bias, const float* residual, int relu, float* out_f32, cudaStream_t stream) {
+  CUtensorMap ta, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tensor_map_2d(&ta_hi, a_hi, rows, K, BM, BK, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&ta_lo, a_lo, rows, K, BM, BK, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&ta, a, rows, K, BM, BK, 4))) return rc;
   if ((rc = make_tensor_map_2d(&tb_hi, w_hi, N, K, BN, BK, 4))) return rc;
   if ((rc = make_tensor_map_2d(&tb_lo, w_lo, N, K, BN, BK, 4))) return rc;
   static std::atomic<bool> configured{false};
@@ -309,21 +322,21 @@ int launch_gemm(const float* a_hi, const float* a_lo, const float* w_hi, const f
   }
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
-  gp.out_f32 = out_f32; gp.out_hi = out_hi; gp.out_lo = out_lo;
-  SSLAM_LAUNCH(KK_GEMM, stream,
-               const int strips = (rows + BM - 1) / BM;
+  gp.out_f32 = out_f32;
+  const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
-  gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
+  SSLAM_LAUNCH(KK_GEMM, stream,
+               gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta, tb_hi, tb_lo, gp));
   return SSLAM_OK;
 }
 
-int launch_layernorm(const float* x, int rows, int W, const float* g, const float* b, float* hi, float* lo,
+int launch_layernorm(const float* x, int rows, int W, const float* g, const float* b, float* out,
                      cudaStream_t stream) {
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   SSLAM_LAUNCH(KK_LAYERNORM, stream,
-               if (W <= 128) layernorm_split_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
-    else if (W <= 384) layernorm_split_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo);
-    else layernorm_split_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, hi, lo));
+               if (W <= 128) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out);
+               else if (W <= 384) layernorm_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out);
+               else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out));
   return SSLAM_OK;
 }
 
@@ -372,11 +385,11 @@ extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int
 }
 
 extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks) {
-  (void)blocks;
+  (void)blocks; (void)C;
   if (rows <= 0) return 0;
   const size_t r = (size_t)rows;
-  // x_hi, x_lo [r,C]; h_a, h_b, u [r,Hd] fp32; t_hi, t_lo, o_hi, o_lo [r,Hd]; raw [r,D]
-  return (2 * r * C + 7 * r * Hd + r * D) * sizeof(float) + 10 * 256;
+  // h_a, h_b, t, u [r,Hd] fp32; raw [r,D]
+  return (4 * r * Hd + r * D) * sizeof(float) + 8 * 256;
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
@@ -391,47 +404,34 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   SSLAM_REQUIRE(params && packed && x && ws && (out_f32 || out_bf16), SSLAM_EINVAL, "refiner: null pointer");
   SSLAM_REQUIRE(C % 4 == 0 && Hd % 4 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
                 "refiner: dims must be multiples of 4 and hidden <= 1024 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
   SSLAM_REQUIRE(ws_bytes >= sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner: workspace %zu < %zu", ws_bytes, sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks));
   const size_t r = (size_t)rows;
   char* wp = static_cast<char*>(ws);
   auto take = [&](size_t floats) { float* q = reinterpret_cast<float*>(wp); wp += align_up(floats * 4, 256); return q; };
-  float* x_hi = take(r * C); float* x_lo = take(r * C);
-  float* h_a = take(r * Hd); float* h_b = take(r * Hd); float* u = take(r * Hd);
-  float* t_hi = take(r * Hd); float* t_lo = take(r * Hd);
-  float* o_hi = take(r * Hd); float* o_lo = take(r * Hd);     // operand pair of the output projection
+  float* h_a = take(r * Hd); float* h_b = take(r * Hd); float* t = take(r * Hd); float* u = take(r * Hd);
   float* raw = take(r * D);
   const float* pk = static_cast<const float*>(packed);
   auto next_w = [&](size_t n, const float*& hi, const float*& lo) { hi = pk; lo = pk + n; pk += 2 * n; };
 
   const float *w_hi, *w_lo;
-  // input projection + ReLU                                              (descriptor_refiner.py:76)
-  if ((rc = launch_split(x, x_hi, x_lo, r * C, stream))) return rc;
-  next_w((size_t)Hd * C, w_hi, w_lo);
-  const bool no_blocks = (blocks == 0);
-  if ((rc = launch_gemm(x_hi, x_lo, w_hi, w_lo, rows, Hd, C, params[1], nullptr, 1,
-                        no_blocks ? nullptr : h_a, no_blocks ? o_hi : nullptr, no_blocks ? o_lo : nullptr, stream)))
-    return rc;
+  next_w((size_t)Hd * C, w_hi, w_lo);                                     // descriptor_refiner.py:76
+  if ((rc = launch_gemm(x, w_hi, w_lo, rows, Hd, C, params[1], nullptr, 1, h_a, stream))) return rc;
   float* h_cur = h_a;
   float* h_nxt = h_b;
   for (int b = 0; b < blocks; ++b) {                                      // :79-80, :108-126
     const float* const* bp = params + 2 + 8 * b;
-    if ((rc = launch_layernorm(h_cur, rows, Hd, bp[0], bp[1], t_hi, t_lo, stream))) return rc;
+    if ((rc = launch_layernorm(h_cur, rows, Hd, bp[0], bp[1], t, stream))) return rc;
     next_w((size_t)Hd * Hd, w_hi, w_lo);
-    if ((rc = launch_gemm(t_hi, t_lo, w_hi, w_lo, rows, Hd, Hd, bp[3], nullptr, 1, u, nullptr, nullptr, stream)))
-      return rc;
-    if ((rc = launch_layernorm(u, rows, Hd, bp[4], bp[5], t_hi, t_lo, stream))) return rc;
+    if ((rc = launch_gemm(t, w_hi, w_lo, rows, Hd, Hd, bp[3], nullptr, 1, u, stream))) return rc;
+    if ((rc = launch_layernorm(u, rows, Hd, bp[4], bp[5], t, stream))) return rc;
     next_w((size_t)Hd * Hd, w_hi, w_lo);
-    const bool last = (b == blocks - 1);
-    // fc2 + identity + ReLU; the last block hands (hi, lo) straight to the output projection
-    if ((rc = launch_gemm(t_hi, t_lo, w_hi, w_lo, rows, Hd, Hd, bp[7], h_cur, 1, last ? nullptr : h_nxt,
-                          last ? o_hi : nullptr, last ? o_lo : nullptr, stream)))
-      return rc;
-    float* t = h_cur; h_cur = h_nxt; h_nxt = t;
+    if ((rc = launch_gemm(t, w_hi, w_lo, rows, Hd, Hd, bp[7], h_cur, 1, h_nxt, stream))) return rc;   // + identity, ReLU
+    float* tmp = h_cur; h_cur = h_nxt; h_nxt = tmp;
   }
   next_w((size_t)D * Hd, w_hi, w_lo);                                     // :83
-  if ((rc = launch_gemm(o_hi, o_lo, w_hi, w_lo, rows, D, Hd, params[3 + 8 * blocks], nullptr, 0, raw, nullptr,
-                        nullptr, stream)))
+  if ((rc = launch_gemm(h_cur, w_hi, w_lo, rows, D, Hd, params[3 + 8 * blocks], nullptr, 0, raw, stream)))
     return rc;
   return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
 }
