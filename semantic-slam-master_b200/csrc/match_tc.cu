@@ -6,9 +6,6 @@
 //   SSLAM_SIM_TF32X3 : "fp32 mode".  Each fp32 operand x is split into hi = tf32(x) and
 //                      lo = tf32(x - hi) (both round-to-nearest, so hi + lo carries ~22 mantissa
 //                      bits) and S = Ah.Bh + Ah.Bl + Al.Bh with kind::tf32, fp32 accumulate in TMEM.
-//                      The split happens in shared memory: TMA loads the raw fp32 tiles and four
-//                      converter warps rewrite them as hi (in place) and lo (adjacent buffer) at the
-//                      same swizzled offsets, so the descriptor bank is read as-is (no copies in HBM).
 //                      The dropped Al.Bl term is <= 2^-22 |a||b|.  The tensor core adds into its fp32
 //                      accumulator with truncation, so the 2^-11-sized cross terms are kept in their
 //                      OWN TMEM accumulator (64 of the 96 MMAs per tile) and added to the Ah.Bh
@@ -43,18 +40,16 @@ namespace {
 
 constexpr int BM = 128, BN = 128;
 constexpr int BLOCK_BYTES = BM * 128;            // one operand tile: 128 rows x 128 bytes of K
-constexpr int CONV_WARPS = 4;                    // tf32x3 only: fp32 -> (hi, lo) split of the staged tiles
+constexpr int NUM_THREADS = 192;
 constexpr int TP_LD = 36;                        // padded row length (floats) of the transpose tile
 
 template <int MODE> struct Cfg;
 template <> struct Cfg<SSLAM_SIM_BF16> {
   static constexpr int TERMS = 1, STAGES = 6, BK = 64, ACC_COLS = BN, TMEM_COLS = 256;
-  static constexpr int NUM_THREADS = 192;
   static constexpr bool TF32 = false;
 };
 template <> struct Cfg<SSLAM_SIM_TF32X3> {
   static constexpr int TERMS = 2, STAGES = 3, BK = 32, ACC_COLS = 2 * BN, TMEM_COLS = 512;
-  static constexpr int NUM_THREADS = 192 + 32 * CONV_WARPS;
   static constexpr bool TF32 = true;
 };
 
@@ -74,13 +69,15 @@ struct SmemLayout {
   static constexpr int OPERANDS = C::STAGES * STAGE_BYTES;
   static constexpr int COLPART = 2 * 4 * BN * 8;                     // [acc][warp][col] u64
   static constexpr int TRANSP = 4 * 32 * TP_LD * 4;                  // [warp][32 rows][TP_LD] fp32
-  static constexpr int BARS = (3 * C::STAGES + 4) * 8 + 16;
+  static constexpr int BARS = (2 * C::STAGES + 4) * 8 + 16;
   static constexpr int TOTAL = OPERANDS + COLPART + TRANSP + BARS + 1024;   // + alignment slack
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::NUM_THREADS, 1)
-match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                TcParams p) {
   using C = Cfg<MODE>;
   using L = SmemLayout<MODE>;
   extern __shared__ unsigned char smem_raw[];
@@ -92,8 +89,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OPERANDS + L::COLPART + L::TRANSP);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::STAGES;
-  uint64_t* conv = bars + 2 * C::STAGES;       // tf32x3: tiles split and visible to the async proxy
-  uint64_t* tfull = bars + 3 * C::STAGES;
+  uint64_t* tfull = bars + 2 * C::STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -104,9 +100,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nkb = (p.D + C::BK - 1) / C::BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], CONV_WARPS);
-    }
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
     fence_barrier_init();
   }
@@ -119,7 +113,8 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      prefetch_tensormap(&tmA); prefetch_tensormap(&tmB);
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmB_hi);
+      if (C::TERMS == 2) { prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_lo); }
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
       const int pair = item / strips;
@@ -131,10 +126,13 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = operands + stage * L::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], 2 * BLOCK_BYTES);     // raw A tile + raw B tile
+          mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
           const int kc = kb * C::BK;
-          tma_load_2d(st, &tmA, &full[stage], kc, a_row);
-          tma_load_2d(st + C::TERMS * BLOCK_BYTES, &tmB, &full[stage], kc, b_row0 + ct * BN);
+          tma_load_2d(st, &tmA_hi, &full[stage], kc, a_row);
+          if (C::TERMS == 2) tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, a_row);
+          tma_load_2d(st + C::TERMS * BLOCK_BYTES, &tmB_hi, &full[stage], kc, b_row0 + ct * BN);
+          if (C::TERMS == 2)
+            tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, b_row0 + ct * BN);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -154,7 +152,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;          // Ah.Bh (or the only term)
         const uint32_t tmem_s = tmem_d + BN;                            // cross terms (tf32x3)
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(C::TERMS == 2 ? &conv[stage] : &full[stage], phase);   // operands ready
+          mbar_wait(&full[stage], phase);                       // TMA bytes have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(operands + stage * L::STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc_sw128(sa);
@@ -178,35 +176,6 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp >= 6) {
-    // ================================ converters (tf32x3 only, warps 6..9) ================================
-    // A and B tiles: fp32 -> tf32 hi (in place) + tf32 lo (next buffer), same swizzled offsets
-    const int cid = (warp - 6) * 32 + lane;
-    int stage = 0; uint32_t phase = 0;
-    const int my_kblocks = ((nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile * nkb;
-    for (int it = 0; it < my_kblocks; ++it) {
-      mbar_wait(&full[stage], phase);
-      float4* base = reinterpret_cast<float4*>(operands + stage * L::STAGE_BYTES);
-#pragma unroll
-      for (int op = 0; op < 2; ++op) {
-        float4* hi = base + op * 2 * (BLOCK_BYTES / 16);
-        float4* lo = hi + BLOCK_BYTES / 16;
-#pragma unroll
-        for (int i = 0; i < BLOCK_BYTES / 16 / (32 * CONV_WARPS); ++i) {
-          const int e = cid + i * 32 * CONV_WARPS;
-          const float4 x = hi[e];
-          float4 h, l;
-          h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
-          l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
-          l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
-          hi[e] = h; lo[e] = l;
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&conv[stage]);
-      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
@@ -314,6 +283,20 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// fp32 -> (tf32 hi, tf32 lo) split of a descriptor bank
+__global__ void split_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ hi,
+                                  float4* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 x = __ldg(src + i), h, l;
+    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+    l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
+    l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
+    hi[i] = h; lo[i] = l;
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -347,10 +330,41 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
 }
 }  // namespace tc
 
-size_t match_tc_extra_workspace(int, int, int, int, int, int, int) { return 0; }
+namespace {
+
+// When bank2 lies inside / directly after bank1 on a frame boundary (sequence mode: bank2 =
+// bank1 + one frame) the two banks are split once, over their union.
+struct BankPlan {
+  bool shared;           // one split region serves both banks
+  size_t frames_a, frames_b, off_b_frames;
+};
+
+BankPlan plan_banks(const float* b1, int F1, const float* b2, int F2, int N, int M, int D) {
+  BankPlan pl{false, (size_t)F1, (size_t)F2, 0};
+  if (N != M) return pl;
+  const size_t frame = (size_t)N * D;
+  const float* end1 = b1 + (size_t)F1 * frame;
+  if (b2 >= b1 && b2 <= end1 && ((size_t)(b2 - b1) % frame) == 0) {
+    pl.shared = true;
+    pl.off_b_frames = (size_t)(b2 - b1) / frame;
+    size_t uni = pl.off_b_frames + (size_t)F2;
+    pl.frames_a = uni > (size_t)F1 ? uni : (size_t)F1;
+  }
+  return pl;
+}
+
+}  // namespace
+
+size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype, int F1, int F2) {
+  (void)P;
+  if (dtype != SSLAM_SIM_TF32X3) return 0;
+  // worst case: both banks split separately (hi + lo each)
+  return 2 * align_up((size_t)F1 * N * D * 4, 256) + 2 * align_up((size_t)F2 * M * D * 4, 256) + 1024;
+}
 
 template <int MODE>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParams& tp, cudaStream_t stream) {
+static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                     const CUtensorMap& b_lo, const TcParams& tp, cudaStream_t stream) {
   using L = SmemLayout<MODE>;
   static std::atomic<bool> configured{false};
   if (!configured.load()) {
@@ -358,32 +372,62 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const TcParam
                                           L::TOTAL));
     configured.store(true);
   }
-  const long long items = (long long)((tp.N + BM - 1) / BM) * tp.P;
-  const int grid = items < num_sms() ? (int)items : num_sms();     // persistent: one CTA per SM
+  const int strips = (tp.N + BM - 1) / BM;
   SSLAM_LAUNCH(KK_MATCH_TC, stream,
-               match_tc_kernel<MODE><<<grid, Cfg<MODE>::NUM_THREADS, L::TOTAL, stream>>>(ta, tb, tp));
+               match_tc_kernel<MODE><<<strips * tp.P, NUM_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp));
   return SSLAM_OK;
 }
 
 int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
                   int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                   u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream) {
-  (void)ws_extra; (void)ws_extra_bytes;
   TcParams tp;
   tp.pair_index = pair_index; tp.P = P; tp.N = N; tp.M = M; tp.D = D;
   tp.nn12 = nn12; tp.best12 = best12; tp.second12 = second12; tp.colkeys = colkeys;
-  CUtensorMap ta, tb;
+  CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   if (dtype == SSLAM_SIM_BF16) {
     SSLAM_REQUIRE(D % 8 == 0, SSLAM_EUNSUPPORTED, "match(bf16): D=%d must be a multiple of 8", D);
-    if ((rc = make_tensor_map_2d(&ta, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
-    if ((rc = make_tensor_map_2d(&tb, bank2, (uint64_t)F2 * M, D, BN, 64, 2))) return rc;
-    return launch_tc<SSLAM_SIM_BF16>(ta, tb, tp, stream);
+    if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, bank2, (uint64_t)F2 * M, D, BN, 64, 2))) return rc;
+    a_lo = a_hi; b_lo = b_hi;
+    return launch_tc<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
-  // tf32x3: the fp32 banks are read as they are; the hi/lo split happens in shared memory
-  if ((rc = make_tensor_map_2d(&ta, bank1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&tb, bank2, (uint64_t)F2 * M, D, BN, 32, 4))) return rc;
-  return launch_tc<SSLAM_SIM_TF32X3>(ta, tb, tp, stream);
+  // ---- tf32x3: split the fp32 banks into hi / lo
+  SSLAM_REQUIRE(ws_extra_bytes >= match_tc_extra_workspace(P, N, M, D, dtype, F1, F2), SSLAM_EWORKSPACE,
+                "match(tf32x3): workspace too small");
+  const float* f1 = static_cast<const float*>(bank1);
+  const float* f2 = static_cast<const float*>(bank2);
+  char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws_extra) + 1023) & ~(uintptr_t)1023);
+  const BankPlan pl = plan_banks(f1, F1, f2, F2, N, M, D);
+  const size_t n1 = pl.frames_a * (size_t)N * D;
+  float* h1 = reinterpret_cast<float*>(w);
+  float* l1 = reinterpret_cast<float*>(w + align_up(n1 * 4, 256));
+  const int sms = num_sms();
+  SSLAM_LAUNCH(KK_SPLIT, stream,
+               split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f1),
+                                                   reinterpret_cast<float4*>(h1), reinterpret_cast<float4*>(l1), n1 / 4));
+  float *h2, *l2;
+  uint64_t rows2;
+  if (pl.shared) {
+    h2 = h1 + pl.off_b_frames * (size_t)N * D;
+    l2 = l1 + pl.off_b_frames * (size_t)N * D;
+    rows2 = (uint64_t)F2 * M;
+  } else {
+    const size_t n2 = (size_t)F2 * M * D;
+    char* w2 = w + 2 * align_up(n1 * 4, 256);
+    h2 = reinterpret_cast<float*>(w2);
+    l2 = reinterpret_cast<float*>(w2 + align_up(n2 * 4, 256));
+    SSLAM_LAUNCH(KK_SPLIT, stream,
+                 split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f2),
+                                                     reinterpret_cast<float4*>(h2), reinterpret_cast<float4*>(l2), n2 / 4));
+    rows2 = (uint64_t)F2 * M;
+  }
+  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, 32, 4))) return rc;
+  return launch_tc<SSLAM_SIM_TF32X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
 }
 
 }  // namespace sslam

@@ -90,6 +90,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int row0 = strip * BM;
+        // pull the next strip's activations from HBM into L2 while this strip is being multiplied
+        // (the A tiles are first-touch HBM reads; everything else this kernel loads is L2 resident)
+        if (strip + (int)gridDim.x < nstrips)
+          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&tmA, kb * BK, (strip + (int)gridDim.x) * BM);
         for (int ct = 0; ct < ntile; ++ct) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
