@@ -70,6 +70,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int nstrips = (p.rows + BM - 1) / BM;       // persistent: strips blockIdx.x, +gridDim.x, ...
   const int ntile = (p.N + BN - 1) / BN;
   const int nkb = (p.K + BK - 1) / BK;
+  // Every CTA multiplies by the same weight matrix; walking its tiles in lock-step would make all
+  // 148 SMs hit the same few L2 lines at once.  Each CTA therefore starts at its own column tile
+  // and its own k-block (the k order only changes the fp32 summation order).
+  const int ct_rot = blockIdx.x % ntile;
+  const int kb_rot = (blockIdx.x / ntile) % nkb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -90,19 +95,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       int stage = 0; uint32_t phase = 0;
       for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int row0 = strip * BM;
-        // pull the next strip's activations from HBM into L2 while this strip is being multiplied
-        // (the A tiles are first-touch HBM reads; everything else this kernel loads is L2 resident)
-        if (strip + (int)gridDim.x < nstrips)
-          for (int kb = 0; kb < nkb; ++kb) tma_prefetch_l2_2d(&tmA, kb * BK, (strip + (int)gridDim.x) * BM);
         for (int ct = 0; ct < ntile; ++ct) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* st = operands + stage * STAGE_BYTES;
             mbar_arrive_expect_tx(&full[stage], TMA_BYTES);
-            const int kc = kb * BK;
+            int kr = kb + kb_rot; if (kr >= nkb) kr -= nkb;
+            int cr = ct + ct_rot; if (cr >= ntile) cr -= ntile;
+            const int kc = kr * BK;
             tma_load_2d(st, &tmA, &full[stage], kc, row0);
-            tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, ct * BN);
-            tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, ct * BN);
+            tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, cr * BN);
+            tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, cr * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -202,7 +205,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
         }
         __syncwarp();
-        const int gc = ct * BN + col0 + sub_c;          // first of this lane's 4 columns
+        int cr = ct + ct_rot; if (cr >= ntile) cr -= ntile;     // same rotation as the producer
+        const int gc = cr * BN + col0 + sub_c;          // first of this lane's 4 columns
         if (gc < p.N) {                                 // N % 4 == 0
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
           float4 res[4];
