@@ -114,6 +114,90 @@ __global__ void __launch_bounds__(SCAN_THREADS) decode_scan_kernel(DecodeParams 
   }
 }
 
+// K1, fast path for radius 1..3: no shared memory.  One warp owns a vertical strip of
+// 32-2R output columns (its 32 lanes load 32 columns, R halo columns per side) and walks down a
+// segment of rows: the horizontal (2R+1)-max comes from warp shuffles, the vertical one from a
+// rolling register window, rows are prefetched PF deep, and local maxima are appended with one
+// atomic per warp-row.  Reads each pixel once from DRAM (halo re-reads are L1/L2 hits).
+template <int R>
+__global__ void __launch_bounds__(256) decode_scan_strip_kernel(DecodeParams p, int nstrips, int nseg,
+                                                                int seg_rows) {
+  constexpr int WIN = 2 * R + 1, OUTW = 32 - 2 * R, PF = 4;
+  const int lane = threadIdx.x & 31;
+  const long long wid = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long per_img = (long long)nstrips * nseg;
+  if (wid >= per_img * p.B) return;
+  const int b = (int)(wid / per_img);
+  const int rem = (int)(wid - (long long)b * per_img);
+  const int seg = rem / nstrips, strip = rem - seg * nstrips;
+  const int H = p.H, W = p.W;
+  const int x = strip * OUTW - R + lane;
+  const bool col_ok = (x >= 0) && (x < W);
+  const bool out_lane = (lane >= R) && (lane < 32 - R) && (x < W);
+  const int y0 = seg * seg_rows, y1 = min(H, y0 + seg_rows);
+  const int y_end = y1 + R;                                   // rows [y0-R, y_end) are loaded
+  const size_t img = (size_t)b * H * W;
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float min_keep = fminf(p.floor, LOWER_FLOOR);
+  ImgHeader* hdr = p.hdr + b;
+  u64* cand = p.cand + (size_t)b * H * W;
+
+  auto ldrow = [&](int y) -> float {
+    return (col_ok && y >= 0 && y < H && y < y_end) ? load_px(p, img + (size_t)y * W + x) : NEG_INF;
+  };
+  float pre[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) pre[i] = ldrow(y0 - R + i);
+  float hwin[WIN], cwin[R + 1];                              // horizontal maxima / centre values
+#pragma unroll
+  for (int i = 0; i < WIN; ++i) hwin[i] = NEG_INF;
+#pragma unroll
+  for (int i = 0; i <= R; ++i) cwin[i] = NEG_INF;
+
+  for (int yy = y0 - R; yy < y_end; yy += PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const int yc = yy + u;
+      const float v = pre[u];
+      pre[u] = ldrow(yc + PF);
+      if (yc < y_end) {                                       // warp-uniform
+        float hm = v;
+#pragma unroll
+        for (int d = 1; d <= R; ++d) {
+          hm = fmaxf(hm, __shfl_up_sync(0xffffffffu, v, d));
+          hm = fmaxf(hm, __shfl_down_sync(0xffffffffu, v, d));
+        }
+#pragma unroll
+        for (int i = 0; i < WIN - 1; ++i) hwin[i] = hwin[i + 1];
+        hwin[WIN - 1] = hm;
+#pragma unroll
+        for (int i = 0; i < R; ++i) cwin[i] = cwin[i + 1];
+        cwin[R] = v;
+        const int yo = yc - R;                                // output row whose window is complete
+        if (yo >= y0) {                                       // warp-uniform
+          float m = hwin[0];
+#pragma unroll
+          for (int i = 1; i < WIN; ++i) m = fmaxf(m, hwin[i]);
+          const float c = cwin[0];
+          const bool is_max = out_lane && (c == m) && (c > min_keep);
+          const unsigned bal = __ballot_sync(0xffffffffu, is_max);
+          if (bal) {
+            const int leader = __ffs(bal) - 1;
+            u32 base = 0;
+            if (lane == leader) base = atomicAdd(&hdr->cand_count, (u32)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (is_max) {
+              const u32 pos = base + __popc(bal & ((1u << lane) - 1));
+              const u32 lin = (u32)(yo * W + x);
+              cand[pos] = ((u64)__float_as_uint(c) << 32) | (u64)(0xffffffffu - lin);
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Plain NMS output (drop-in for _apply_nms)
 __global__ void __launch_bounds__(SCAN_THREADS) nms_kernel(const float* sal, int H, int W, int r,
                                                            float* out) {
@@ -443,10 +527,23 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
   SSLAM_CHECK_CUDA(cudaMemsetAsync(p.hdr, 0, (size_t)B * sizeof(ImgHeader), stream));
 
   const int r = nms_radius;
-  size_t scan_smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
-  dim3 g1((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
-  SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
-               decode_scan_kernel<<<g1, SCAN_THREADS, scan_smem, stream>>>(p));
+  if (r >= 1 && r <= 3) {
+    const int outw = 32 - 2 * r;
+    const int nstrips = (W + outw - 1) / outw;
+    int nseg = (H + 63) / 64;                                  // ~64 rows per warp
+    const int seg_rows = (H + nseg - 1) / nseg;
+    nseg = (H + seg_rows - 1) / seg_rows;
+    const long long warps = (long long)nstrips * nseg * B;
+    const unsigned blocks = (unsigned)((warps + 7) / 8);
+    SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
+                 if (r == 1) decode_scan_strip_kernel<1><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows);
+                 else if (r == 2) decode_scan_strip_kernel<2><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows);
+                 else decode_scan_strip_kernel<3><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows));
+  } else {
+    size_t scan_smem = (size_t)((TILE_H + 2 * r) * (TILE_W + 2 * r) + (TILE_H + 2 * r) * TILE_W) * 4;
+    dim3 g1((W + TILE_W - 1) / TILE_W, (H + TILE_H - 1) / TILE_H, B);
+    SSLAM_LAUNCH(KK_DECODE_SCAN, stream, decode_scan_kernel<<<g1, SCAN_THREADS, scan_smem, stream>>>(p));
+  }
 
   const int kpad = next_pow2(K);
   size_t sel_smem = (size_t)kpad * 8 + sizeof(SelectScratch);
