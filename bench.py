@@ -122,10 +122,26 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         if not self.ok or not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+            return smi_clocks(self.index)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def smi_clocks(index):
+    """Fallback when NVML sampling failed: one nvidia-smi query right after the timed region."""
+    import subprocess
+    try:
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for n, v in zip(names, out[2:]) if v.strip().lower() == "active"]
+        return {"sm_mhz": int(out[0]), "sm_max_mhz": int(out[1]), "reasons": reasons,
+                "note": "NVML sampling unavailable; single nvidia-smi sample after the timed region"}
+    except Exception as e:                                                # pragma: no cover
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": f"no clock source: {e!r}"}
 
 
 def physical_gpu_index(local):
