@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=600)
     ap.add_argument("--kpts", type=int, default=2048)
-    ap.add_argument("--mode", default="auto", choices=["auto", "f32", "tf32x3", "bf16"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "f32", "tf32x3", "f16x3", "bf16"])
     ap.add_argument("--chunk", type=int, default=64)
     ap.add_argument("--cpu-sample-frames", type=int, default=33)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -215,7 +215,7 @@ def run_b200(a):
     if mode_name == "auto":
         # "fp32 mode" of BASELINE config c2: fp32 in/out, 3-term TF32 split on the tensor cores
         mode_name = os.environ.get("SSLAM_BENCH_MODE", "tf32x3")
-    mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16}[mode_name]
+    mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16, "f16x3": ops.SIM_F16X3}[mode_name]
 
     torch.manual_seed(0)
     refiner = DescriptorRefiner(C, 384, D, 4).to(dev)
@@ -380,7 +380,7 @@ def run_b200(a):
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"f32": "f32", "tf32x3": "tf32x3 (fp32 in/out)", "bf16": "bf16"}[mode_name],
+            "vs_baseline": None, "dtype": {"f32": "f32", "tf32x3": "tf32x3 (fp32 in/out)", "f16x3": "f16x3 (fp32 in/out)", "bf16": "bf16"}[mode_name],
             "data": "synthetic",
             "config": {"workload": workload_name(a), "frames_per_rank": T, "pairs_per_step": pairs_per_step,
                        "similarity_mode": mode_name, "chunk": a.chunk,

@@ -53,7 +53,11 @@ enum {
 enum {
   SSLAM_SIM_F32 = 0,    /* fp32 FMA on CUDA cores (exact-mode reference implementation)          */
   SSLAM_SIM_TF32X3 = 1, /* tcgen05 kind::tf32, 3-term hi/lo split, fp32 accumulate in TMEM       */
-  SSLAM_SIM_BF16 = 2    /* tcgen05 kind::f16 on bf16 copies, fp32 accumulate in TMEM             */
+  SSLAM_SIM_BF16 = 2,   /* tcgen05 kind::f16 on bf16 copies, fp32 accumulate in TMEM             */
+  SSLAM_SIM_F16X3 = 3   /* fp32 in/out; x = hi + lo*2^-11 with hi, lo fp16 (22 mantissa bits), three
+                           kind::f16 MMAs (hi.hi, hi.lo, lo.hi) at the full 16-bit tensor rate, fp32
+                           accumulate in TMEM; same accuracy class as TF32X3 at half the tensor time
+                           and half the operand bytes.  Requires |x| < 65504.                   */
 };
 
 /* acceptance rule for sslam_match_finalize; params[] meaning per variant */
@@ -154,7 +158,7 @@ int sslam_refiner_forward_f32(const float* const* params, const void* packed, co
  * bank1 holds F1 descriptor sets [F1,N,D], bank2 holds F2 sets [F2,M,D] (the banks may alias, e.g.
  * bank2 = bank1 + N*D for consecutive-frame matching).  Pair p reads set a of bank1 and set b of
  * bank2 where (a,b) = pair_index[p] if pair_index != NULL (int32 [P,2], device) else (p,p).  `dtype` is SSLAM_SIM_*; banks are fp32 for
- * SSLAM_SIM_F32 / SSLAM_SIM_TF32X3 and bf16 for SSLAM_SIM_BF16.  D % 4 == 0, D <= 256.
+ * SSLAM_SIM_F32 / TF32X3 / F16X3 and bf16 for SSLAM_SIM_BF16.  D % 4 == 0 (8 for bf16/f16x3), D <= 256.
  * Replaces visualize_matches.py:105-109,117-119; visualize_matches_sequence.py:144-146;
  * test/test_descriptor_quality.py:116-130; train.py:422-424; test/test_tracking.py:159-160.
  */

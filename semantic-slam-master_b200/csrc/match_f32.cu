@@ -327,7 +327,8 @@ extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, in
   SSLAM_REQUIRE(bank1 && bank2 && nn12 && best12 && second12 && nn21 && best21 && ws, SSLAM_EINVAL,
                 "match: null pointer");
   SSLAM_REQUIRE(D % 4 == 0 && D <= MAX_D, SSLAM_EUNSUPPORTED, "match: D=%d (need D%%4==0, D<=256)", D);
-  SSLAM_REQUIRE(dtype == SSLAM_SIM_F32 || dtype == SSLAM_SIM_TF32X3 || dtype == SSLAM_SIM_BF16,
+  SSLAM_REQUIRE(dtype == SSLAM_SIM_F32 || dtype == SSLAM_SIM_TF32X3 || dtype == SSLAM_SIM_BF16 ||
+                    dtype == SSLAM_SIM_F16X3,
                 SSLAM_EINVAL, "match: unknown dtype %d", dtype);
   SSLAM_REQUIRE(F1 > 0 && F2 > 0 && (pair_index || (F1 >= P && F2 >= P)), SSLAM_EINVAL,
                 "match: banks hold %d / %d sets but %d implicit pairs were requested", F1, F2, P);

@@ -47,10 +47,20 @@ template <int MODE> struct Cfg;
 template <> struct Cfg<SSLAM_SIM_BF16> {
   static constexpr int TERMS = 1, STAGES = 6, BK = 64, ACC_COLS = BN, TMEM_COLS = 256;
   static constexpr bool TF32 = false;
+  static constexpr uint32_t FMT = FMT_BF16;
+  static constexpr float CROSS_SCALE = 1.0f;
 };
 template <> struct Cfg<SSLAM_SIM_TF32X3> {
   static constexpr int TERMS = 2, STAGES = 3, BK = 32, ACC_COLS = 2 * BN, TMEM_COLS = 512;
   static constexpr bool TF32 = true;
+  static constexpr uint32_t FMT = FMT_TF32;
+  static constexpr float CROSS_SCALE = 1.0f;
+};
+template <> struct Cfg<SSLAM_SIM_F16X3> {            // hi/lo are fp16, lo carries a 2^11 scale
+  static constexpr int TERMS = 2, STAGES = 3, BK = 64, ACC_COLS = 2 * BN, TMEM_COLS = 512;
+  static constexpr bool TF32 = false;
+  static constexpr uint32_t FMT = FMT_F16;
+  static constexpr float CROSS_SCALE = 1.0f / 2048.0f;
 };
 
 struct TcParams {
@@ -141,7 +151,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (elect_one()) {
-      const uint32_t idesc = make_instr_desc(C::TF32 ? FMT_TF32 : FMT_BF16, BM, BN);
+      const uint32_t idesc = make_instr_desc(C::FMT, BM, BN);
       int stage = 0; uint32_t phase = 0;
       const int my_tiles = ((nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile;
       for (int tc = 0; tc < my_tiles; ++tc) {                   // tc: running tile count of this CTA
@@ -212,7 +222,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            r[j] = __float_as_uint(__fadd_rn(__uint_as_float(r[j]), __uint_as_float(rs[j])));
+            r[j] = __float_as_uint(__fmaf_rn(__uint_as_float(rs[j]), C::CROSS_SCALE, __uint_as_float(r[j])));
         } else {
           tmem_ld_wait();
         }
@@ -297,6 +307,21 @@ __global__ void split_tf32_kernel(const float4* __restrict__ src, float4* __rest
   }
 }
 
+// fp32 -> (fp16 hi, fp16 lo * 2^11) split of a descriptor bank
+__global__ void split_f16_kernel(const float4* __restrict__ src, uint2* __restrict__ hi,
+                                 uint2* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    const float4 x = __ldg(src + i);
+    __half h[4], l[4];
+    split_f16(x.x, h[0], l[0]); split_f16(x.y, h[1], l[1]);
+    split_f16(x.z, h[2], l[2]); split_f16(x.w, h[3], l[3]);
+    hi[i] = *reinterpret_cast<uint2*>(h);
+    lo[i] = *reinterpret_cast<uint2*>(l);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -321,6 +346,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // 2-byte elements are moved as opaque 16-bit words (bf16 and fp16 alike)
   CUresult r = g_encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -357,9 +383,10 @@ BankPlan plan_banks(const float* b1, int F1, const float* b2, int F2, int N, int
 
 size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype, int F1, int F2) {
   (void)P;
-  if (dtype != SSLAM_SIM_TF32X3) return 0;
-  // worst case: both banks split separately (hi + lo each)
-  return 2 * align_up((size_t)F1 * N * D * 4, 256) + 2 * align_up((size_t)F2 * M * D * 4, 256) + 1024;
+  if (dtype != SSLAM_SIM_TF32X3 && dtype != SSLAM_SIM_F16X3) return 0;
+  // worst case: both banks split separately (hi + lo each); fp16 pairs take half the bytes
+  const size_t e = dtype == SSLAM_SIM_F16X3 ? 2 : 4;
+  return 2 * align_up((size_t)F1 * N * D * e, 256) + 2 * align_up((size_t)F2 * M * D * e, 256) + 1024;
 }
 
 template <int MODE>
@@ -393,40 +420,52 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
     a_lo = a_hi; b_lo = b_hi;
     return launch_tc<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
-  // ---- tf32x3: split the fp32 banks into hi / lo
+  // ---- split modes: the fp32 banks are split into hi / lo (tf32 pairs or fp16 pairs)
+  const bool f16 = (dtype == SSLAM_SIM_F16X3);
+  const size_t e = f16 ? 2 : 4;
+  SSLAM_REQUIRE(!f16 || D % 8 == 0, SSLAM_EUNSUPPORTED, "match(f16x3): D=%d must be a multiple of 8", D);
   SSLAM_REQUIRE(ws_extra_bytes >= match_tc_extra_workspace(P, N, M, D, dtype, F1, F2), SSLAM_EWORKSPACE,
-                "match(tf32x3): workspace too small");
+                "match(split): workspace too small");
   const float* f1 = static_cast<const float*>(bank1);
   const float* f2 = static_cast<const float*>(bank2);
   char* w = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(ws_extra) + 1023) & ~(uintptr_t)1023);
   const BankPlan pl = plan_banks(f1, F1, f2, F2, N, M, D);
   const size_t n1 = pl.frames_a * (size_t)N * D;
-  float* h1 = reinterpret_cast<float*>(w);
-  float* l1 = reinterpret_cast<float*>(w + align_up(n1 * 4, 256));
+  char* h1 = w;
+  char* l1 = w + align_up(n1 * e, 256);
   const int sms = num_sms();
-  SSLAM_LAUNCH(KK_SPLIT, stream,
-               split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f1),
-                                                   reinterpret_cast<float4*>(h1), reinterpret_cast<float4*>(l1), n1 / 4));
-  float *h2, *l2;
-  uint64_t rows2;
+  auto split = [&](const float* src, char* hi, char* lo, size_t n) -> int {
+    if (f16)
+      SSLAM_LAUNCH(KK_SPLIT, stream,
+                   split_f16_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                                 reinterpret_cast<uint2*>(hi),
+                                                                 reinterpret_cast<uint2*>(lo), n / 4));
+    else
+      SSLAM_LAUNCH(KK_SPLIT, stream,
+                   split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                                  reinterpret_cast<float4*>(hi),
+                                                                  reinterpret_cast<float4*>(lo), n / 4));
+    return SSLAM_OK;
+  };
+  if ((rc = split(f1, h1, l1, n1))) return rc;
+  char *h2, *l2;
   if (pl.shared) {
-    h2 = h1 + pl.off_b_frames * (size_t)N * D;
-    l2 = l1 + pl.off_b_frames * (size_t)N * D;
-    rows2 = (uint64_t)F2 * M;
+    h2 = h1 + pl.off_b_frames * (size_t)N * D * e;
+    l2 = l1 + pl.off_b_frames * (size_t)N * D * e;
   } else {
     const size_t n2 = (size_t)F2 * M * D;
-    char* w2 = w + 2 * align_up(n1 * 4, 256);
-    h2 = reinterpret_cast<float*>(w2);
-    l2 = reinterpret_cast<float*>(w2 + align_up(n2 * 4, 256));
-    SSLAM_LAUNCH(KK_SPLIT, stream,
-                 split_tf32_kernel<<<sms * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(f2),
-                                                     reinterpret_cast<float4*>(h2), reinterpret_cast<float4*>(l2), n2 / 4));
-    rows2 = (uint64_t)F2 * M;
+    char* w2 = w + 2 * align_up(n1 * e, 256);
+    h2 = w2;
+    l2 = w2 + align_up(n2 * e, 256);
+    if ((rc = split(f2, h2, l2, n2))) return rc;
   }
-  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, 32, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, 32, 4))) return rc;
+  const uint64_t rows2 = (uint64_t)F2 * M;
+  const uint32_t bk = f16 ? 64 : 32;
+  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, bk, (int)e))) return rc;
+  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, bk, (int)e))) return rc;
+  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, bk, (int)e))) return rc;
+  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, bk, (int)e))) return rc;
+  if (f16) return launch_tc<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   return launch_tc<SSLAM_SIM_TF32X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
 }
 

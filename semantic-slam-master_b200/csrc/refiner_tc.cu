@@ -20,6 +20,8 @@
 // inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
 // store epilogue of a strip overlaps the MMAs of the next.  Activations round-trip
 // HBM between layers (rows x 384 fp32); the whole chain is ~10 launches per call.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace sslam {
@@ -49,6 +51,7 @@ struct GemmParams {
   const float* residual;    // [rows, N] or null
   int relu;
   float* out_f32;           // [rows, N]
+  int dbg;                  // tuning experiments only (SSLAM_GEMM_DBG): 1 no stores, 2 no split math, 4 no MMA
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -130,6 +133,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
           const uint64_t b_hi = make_smem_desc_sw128(sa + 2 * BLOCK_BYTES);
           const uint64_t b_lo = make_smem_desc_sw128(sa + 3 * BLOCK_BYTES);
+          if (!(p.dbg & 4))
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -154,6 +158,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(&full[stage], phase);
       float4* a = reinterpret_cast<float4*>(operands + stage * STAGE_BYTES);
       float4* alo = a + BLOCK_BYTES / 16;
+      if (!(p.dbg & 2))
 #pragma unroll
       for (int i = 0; i < BLOCK_BYTES / 16 / (32 * CONV_WARPS); ++i) {
         const int e = cid + i * 32 * CONV_WARPS;
@@ -234,7 +239,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               if (p.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (!(p.dbg & 1)) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
             }
           }
         }
@@ -331,6 +336,8 @@ int launch_gemm(const float* a, const float* w_hi, const float* w_lo, int rows, 
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
   gp.out_f32 = out_f32;
+  static const int dbg = getenv("SSLAM_GEMM_DBG") ? atoi(getenv("SSLAM_GEMM_DBG")) : 0;
+  gp.dbg = dbg;
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,

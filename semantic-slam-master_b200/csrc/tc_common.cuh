@@ -4,7 +4,9 @@
 // LDTM, UTMALDG, SYNCS).
 #pragma once
 
-#include <cuda.h>   // CUtensorMap (types only; the driver entry point is fetched at run time)
+#include <cuda.h>   // CUtensorMap
+#include <cuda_fp16.h>
+// (types only; the driver entry point is fetched at run time)
 
 #include "common.cuh"
 
@@ -161,7 +163,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor (32 bit) for kind::f16 / kind::tf32, dense, fp32 accumulate, both
 // operands K-major:  [4,6) D format 1=f32   [7,10) A format   [10,13) B format
 //   (0 f16, 1 bf16, 2 tf32)   [15] A major 0=K   [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
-constexpr uint32_t FMT_BF16 = 1, FMT_TF32 = 2;
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1, FMT_TF32 = 2;
 __host__ __device__ constexpr uint32_t make_instr_desc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
@@ -198,6 +200,15 @@ __device__ __forceinline__ float to_tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
+}
+// fp32 -> (fp16 hi, fp16 lo) with x ~= hi + lo * 2^-11 (22 significant bits)
+constexpr float F16_LO_SCALE = 2048.0f, F16_LO_INV = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(__fmul_rn(__fsub_rn(x, __half2float(hi)), F16_LO_SCALE));
+}
+__device__ __forceinline__ float join_f16(__half hi, __half lo) {
+  return __fmaf_rn(__half2float(lo), F16_LO_INV, __half2float(hi));
 }
 #endif  // __CUDACC__
 

@@ -11,4 +11,4 @@ sm_100 device is missing.
 from . import _lib  # noqa: F401
 from .ops import (decode_topk, nms, gather_bilinear, l2norm_rows, match_top2, match_finalize,  # noqa: F401
                   RefinerPlan, refiner_forward,
-                  SIM_F32, SIM_TF32X3, SIM_BF16, M1, M2, M3, M4, M5, launch_count)
+                  SIM_F32, SIM_TF32X3, SIM_BF16, SIM_F16X3, M1, M2, M3, M4, M5, launch_count)

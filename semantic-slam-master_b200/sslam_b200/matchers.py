@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .ops import M1, M2, M3, M4, M5, SIM_F32, SIM_BF16, SIM_TF32X3  # noqa: F401
+from .ops import M1, M2, M3, M4, M5, SIM_F32, SIM_BF16, SIM_TF32X3, SIM_F16X3  # noqa: F401
 
 
 def _f32(x):

@@ -7,7 +7,7 @@ import torch
 
 from . import _lib
 
-SIM_F32, SIM_TF32X3, SIM_BF16 = 0, 1, 2
+SIM_F32, SIM_TF32X3, SIM_BF16, SIM_F16X3 = 0, 1, 2, 3
 M1, M2, M3, M4, M5 = 1, 2, 3, 4, 5
 
 

@@ -69,6 +69,19 @@ def test_tf32x3_top2(n, m, d, dev):
 
 
 @pytest.mark.parametrize("n,m,d", [c for c in CASES if c[2] % 8 == 0])
+def test_f16x3_top2(n, m, d, dev):
+    """fp32 mode on the 16-bit tensor pipe: x = hi + lo*2^-11 (fp16 pair), three MMAs."""
+    from sslam_b200 import ops
+    d1, d2, _ = recipes.descriptor_pair(n, m, d, 300 + n + m, noise=3, dup_every=11)
+    top = ops.match_top2(cu(d1[None], dev), cu(d2[None], dev), mode=ops.SIM_F16X3)
+    t = {k: v[0].cpu().numpy() for k, v in top.items()}
+    S64 = d1.astype(np.float64) @ d2.astype(np.float64).T
+    exc = check_top(t, S64, 3e-6, 1e-6)
+    print(f"f16x3 {n}x{m}x{d}: near-tie index exceptions {exc}, "
+          f"max |best-S| {np.abs(t['best12'] - S64.max(1)).max():.2e}")
+
+
+@pytest.mark.parametrize("n,m,d", [c for c in CASES if c[2] % 8 == 0])
 def test_bf16_top2(n, m, d, dev):
     from sslam_b200 import ops
     d1, d2, _ = recipes.descriptor_pair(n, m, d, 400 + n + m, noise=3)
@@ -91,12 +104,12 @@ def test_tc_pair_index_and_aliasing(dev):
     bank = np.stack([recipes.descriptor_pair(N, N, D, 500 + f, noise=2)[f % 2] for f in range(F)])
     b32 = cu(bank, dev)
     ref = ops.match_top2(b32, b32[1:], mode=ops.SIM_F32, num_pairs=F - 1)
-    for mode, bk in ((ops.SIM_TF32X3, b32), (ops.SIM_BF16, b32.to(torch.bfloat16))):
+    for mode, bk in ((ops.SIM_TF32X3, b32), (ops.SIM_F16X3, b32), (ops.SIM_BF16, b32.to(torch.bfloat16))):
         top = ops.match_top2(bk, bk[1:], mode=mode, num_pairs=F - 1)
-        tol = 2e-6 if mode == ops.SIM_TF32X3 else 2e-2
+        tol = 2e-6 if mode != ops.SIM_BF16 else 2e-2
         assert torch.allclose(top["best12"], ref["best12"], atol=tol, rtol=0)
         assert torch.allclose(top["best21"], ref["best21"], atol=tol, rtol=0)
-        if mode == ops.SIM_TF32X3:
+        if mode != ops.SIM_BF16:
             agree = (top["nn12"] == ref["nn12"]).float().mean().item()
             assert agree > 0.999
         idx = torch.tensor([[4, 0], [2, 2], [0, 3]], dtype=torch.int32, device=dev)
@@ -105,8 +118,9 @@ def test_tc_pair_index_and_aliasing(dev):
         assert torch.allclose(a["best12"], r["best12"], atol=tol, rtol=0)
 
 
-def test_tf32x3_sequence_matches_vs_oracle(dev):
-    """c2-shaped: 3 frames 640x480, K=2048, D=256, consecutive pairs, fp32 (tf32x3) mode."""
+@pytest.mark.parametrize("mode_name", ["tf32x3", "f16x3"])
+def test_fp32_mode_sequence_matches_vs_oracle(mode_name, dev):
+    """c2-shaped: 3 frames 640x480, K=2048, D=256, consecutive pairs, fp32 modes on tensor cores."""
     from models.descriptor_refiner import DescriptorRefiner
     from sslam_b200 import matchers, ops, synth
     from sslam_b200.pipeline import FrontEnd
@@ -114,7 +128,8 @@ def test_tf32x3_sequence_matches_vs_oracle(dev):
     refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
     T, K = 3, 2048
     sal, feat = synth.make_sequence(T, seq_id=1)
-    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel", sim_mode=ops.SIM_TF32X3)
+    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel",
+                  sim_mode={"tf32x3": ops.SIM_TF32X3, "f16x3": ops.SIM_F16X3}[mode_name])
     feats, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1)
     d = feats["descriptors"].cpu().numpy()
     sc = feats["scores"].cpu().numpy()
@@ -129,7 +144,7 @@ def test_tf32x3_sequence_matches_vs_oracle(dev):
         exc += compare_matches(S, rm, p2[p, :int(c2[p])].cpu().numpy(),
                                threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
         assert int(counts[p]) > K // 4
-    print("tf32x3 sequence near-tie exceptions:", exc)
+    print(mode_name, "sequence near-tie exceptions:", exc)
 
 
 def test_bf16_sequence_scores(dev):
