@@ -7,8 +7,9 @@
 Workload (BASELINE.json configs[1], "c2"): a TUM-RGB-D-shaped synthetic sequence of 600 frames,
 640x480 saliency maps + 30x40x384 NHWC feature maps already past the backbone, K = 2048 keypoints,
 D = 256, consecutive-pair matching with matcher M1 (ratio 0.8), fp32 mode (descriptors fp32; the
-similarity and the refiner GEMMs run as 3-term TF32 splits on tcgen05, error < 3e-6 — `--mode f32`
-selects the CUDA-core exact kernel, `--mode bf16` the bf16 similarity of config c3).  One *step* is one
+similarity and the refiner GEMMs run as 3-term fp16 hi/lo splits on tcgen05, error < 3e-6 —
+`--mode tf32x3` is the TF32 variant, `--mode f32` the CUDA-core exact kernel, `--mode bf16` the bf16
+similarity of config c3).  One *step* is one
 pass over the whole sequence: every frame is extracted once (decode -> sample -> refiner MLP ->
 L2 norm) and each of the 599 consecutive pairs is matched.  With N GPUs every rank processes its
 own 600-frame sequence (weak scaling) and the match lists are gathered on rank 0 over NCCL.
@@ -36,7 +37,7 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 _REAL_STDOUT = None
-# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_tf32x3 launch (131072 x 384 x 384), from
+# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_f16x3 launch (131072 x 384 x 384), from
 # the committed `ncu --set full` capture in profiles/ (None until re-captured for the current kernel)
 NCU_GEMM_DRAM_BYTES_PER_LAUNCH = None
 
@@ -213,8 +214,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=dev)
     mode_name = a.mode
     if mode_name == "auto":
-        # "fp32 mode" of BASELINE config c2: fp32 in/out, 3-term TF32 split on the tensor cores
-        mode_name = os.environ.get("SSLAM_BENCH_MODE", "tf32x3")
+        # "fp32 mode" of BASELINE config c2: fp32 in/out, 3-term fp16 hi/lo split on the tensor cores
+        mode_name = os.environ.get("SSLAM_BENCH_MODE", "f16x3")
     mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16, "f16x3": ops.SIM_F16X3}[mode_name]
 
     torch.manual_seed(0)
@@ -324,7 +325,7 @@ def run_b200(a):
     rows = T * a.kpts
     blocks = 2
     work = {   # algorithmic work per step of each kernel kind
-        "gemm_tf32x3": ("tensor", 2.0 * rows * (C * 384 + blocks * 2 * 384 * 384 + 384 * D)),
+        "gemm_f16x3": ("tensor", 2.0 * rows * (C * 384 + blocks * 2 * 384 * 384 + 384 * D)),
         "match_tc": ("tensor", 2.0 * a.kpts * a.kpts * D * (T - 1)),
         "match_f32": ("tensor", 2.0 * a.kpts * a.kpts * D * (T - 1)),
         "decode_scan": ("hbm", (4.0 * H * W + 12 * a.kpts) * T),
@@ -347,9 +348,9 @@ def run_b200(a):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
     # dram bytes per launch from the committed `ncu --set full` capture (profiles/), where available
-    ncu_traffic = {"gemm_tf32x3": NCU_GEMM_DRAM_BYTES_PER_LAUNCH * (a.chunk / 64.0) if NCU_GEMM_DRAM_BYTES_PER_LAUNCH else None}
-    tf32_note = ("fp32 mode issues 3 TF32 MMAs per product and TF32 runs at half the bf16 rate, so the "
-                 "ceiling of this fraction is 1/6 = 0.167")
+    ncu_traffic = {"gemm_f16x3": NCU_GEMM_DRAM_BYTES_PER_LAUNCH * (a.chunk / 64.0) if NCU_GEMM_DRAM_BYTES_PER_LAUNCH else None}
+    tf32_note = ("fp32 accuracy costs three 16-bit MMAs per product (fp16 hi/lo split), so the ceiling of "
+                 "this fraction is 1/3 = 0.333 (1/6 for the tf32x3 variant)")
     if work.get(dom, ("", 0))[0] == "tensor":
         ach = dk["algorithmic_TFLOP/s"]
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
@@ -360,7 +361,7 @@ def run_b200(a):
                     "algorithmic_flops_per_step": work[dom][1],
                     "note": ("achieved = algorithmic flops of all launches of this kernel in a step / their "
                              "summed CUDA-event durations (instrumented pass of the same steps); "
-                             + (tf32_note if mode_name != "bf16" or dom == "gemm_tf32x3" else ""))}
+                             + (tf32_note if mode_name != "bf16" or dom == "gemm_f16x3" else ""))}
     else:
         ach = dk.get("algorithmic_GB/s", float("nan"))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",

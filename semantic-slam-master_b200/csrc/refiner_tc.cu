@@ -2,24 +2,26 @@
 //
 // Replaces the body of DescriptorRefiner.forward / ResidualBlock.forward
 // (models/descriptor_refiner.py:73-86, 108-126): Linear+ReLU, [LN, Linear+ReLU, LN, Linear,
-// +identity, ReLU] x blocks, Linear, L2 normalise — with fp32-level accuracy:
+// +identity, ReLU] x blocks, Linear, L2 normalise — with fp32-level accuracy at the full 16-bit
+// tensor-core rate:
 //
-//   * every Linear is a tcgen05 kind::tf32 GEMM in the 3-term hi/lo split
-//     (x = hi + lo, both round-to-nearest tf32;  x.w ~= hi.hi' + hi.lo' + lo.hi'), operands fed by
-//     TMA into 128B-swizzled smem, accumulators in TMEM.  As in match_tc.cu the small cross terms
-//     get their own accumulator so that the tensor core's truncating accumulate does not eat them.
-//   * activations stay plain fp32 in HBM: the A tile is TMA-loaded raw and four converter warps
-//     split it in shared memory (hi in place, lo next to it, same swizzled offsets) before the MMA
-//     warp consumes it, so no (hi, lo) copies of activations ever touch HBM; weights are split
-//     once by sslam_refiner_pack_weights.
-//   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes
-//     fp32 through a smem transpose so that global stores are coalesced.
-//   * LayerNorm is a warp-per-row fp32 kernel.
+//   * numbers are carried as fp16 PAIRS, x ~= hi + lo * 2^-11 (hi = fp16(x), lo = fp16((x-hi) * 2^11):
+//     22 significant bits), and every Linear is three tcgen05 kind::f16 MMAs
+//         x.w ~= hi.hi'  +  2^-11 * (hi.lo' + lo.hi')
+//     with fp32 accumulation in TMEM; the cross terms live in their own accumulator and are folded
+//     in by the epilogue with one FMA (the tensor core truncates when it adds into an accumulator,
+//     so small terms must not be added to a large one inside it).  The dropped lo.lo' term is 2^-22.
+//   * activations travel between layers as such pairs (two fp16 arrays = 4 bytes per element, the
+//     same HBM traffic as fp32) and are loaded by TMA straight into 128B-swizzled operand tiles —
+//     no conversion stage, no fp32 activations in HBM; weights are split once by
+//     sslam_refiner_pack_weights.  Requires |activation| < 65504.
+//   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes the
+//     next layer's pair (or fp32 for the last layer) through a smem transpose, coalesced.
+//   * LayerNorm is a warp-per-row kernel, pair in, pair out.
 //
 // Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
 // inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
-// store epilogue of a strip overlaps the MMAs of the next.  Activations round-trip
-// HBM between layers (rows x 384 fp32); the whole chain is ~10 launches per call.
+// store epilogue of a strip overlaps the MMAs of the next.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -30,33 +32,34 @@ using namespace tc;
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 32;               // BK fp32 = 128 bytes of K
+constexpr int BM = 128, BN = 128, BK = 64;               // BK fp16 = 128 bytes of K
 constexpr int BLOCK_BYTES = BM * 128;
 constexpr int STAGES = 3;
-constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A (raw -> hi), A_lo, B_hi, B_lo
-constexpr int TMA_BYTES = 3 * BLOCK_BYTES;               // A raw, B_hi, B_lo arrive by TMA
+constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A_hi, A_lo, B_hi, B_lo
 constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter
-constexpr int CONV_WARPS = 4;                            // fp32 -> (tf32 hi, tf32 lo) split of the A tile
-constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS + 32 * CONV_WARPS;
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 cross)
 constexpr int TP_LD = 20;                                // 16 columns + 4 pad (floats)
 constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
 constexpr int SMEM_TRANSP = EPI_WARPS * 32 * TP_LD * 4;
-constexpr int SMEM_BARS = (3 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
 constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_BARS + 1024;
 
 struct GemmParams {
   int rows, N, K;
   const float* bias;        // [N]
-  const float* residual;    // [rows, N] or null
+  const __half* res_hi;     // residual pair [rows, N] or null
+  const __half* res_lo;
   int relu;
-  float* out_f32;           // [rows, N]
-  int dbg;                  // tuning experiments only (SSLAM_GEMM_DBG): 1 no stores, 2 no split math, 4 no MMA
+  float* out_f32;           // [rows, N] or null
+  __half* out_hi;           // pair [rows, N] or null
+  __half* out_lo;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB_hi,
-                   const __grid_constant__ CUtensorMap tmB_lo, GemmParams p) {
+gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                  GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* operands = smem;
@@ -64,8 +67,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* conv = bars + 2 * STAGES;                    // A tile split and visible to the async proxy
-  uint64_t* tfull = bars + 3 * STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
@@ -80,9 +82,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int kb_rot = (blockIdx.x / ntile) % nkb;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], CONV_WARPS);
-    }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     fence_barrier_init();
   }
@@ -94,7 +94,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
   if (warp == 0) {
     if (elect_one()) {                                            // ---- TMA producer
-      prefetch_tensormap(&tmA); prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
+      prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
       int stage = 0; uint32_t phase = 0;
       for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int row0 = strip * BM;
@@ -102,11 +103,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* st = operands + stage * STAGE_BYTES;
-            mbar_arrive_expect_tx(&full[stage], TMA_BYTES);
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
             int kr = kb + kb_rot; if (kr >= nkb) kr -= nkb;
             int cr = ct + ct_rot; if (cr >= ntile) cr -= ntile;
             const int kc = kr * BK;
-            tma_load_2d(st, &tmA, &full[stage], kc, row0);
+            tma_load_2d(st, &tmA_hi, &full[stage], kc, row0);
+            tma_load_2d(st + BLOCK_BYTES, &tmA_lo, &full[stage], kc, row0);
             tma_load_2d(st + 2 * BLOCK_BYTES, &tmB_hi, &full[stage], kc, cr * BN);
             tma_load_2d(st + 3 * BLOCK_BYTES, &tmB_lo, &full[stage], kc, cr * BN);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -116,7 +118,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {                                            // ---- MMA issuer
-      const uint32_t idesc = make_instr_desc(FMT_TF32, BM, BN);
+      const uint32_t idesc = make_instr_desc(FMT_F16, BM, BN);
       int stage = 0; uint32_t phase = 0;
       const int my_tiles = ((nstrips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile;
       for (int tc = 0; tc < my_tiles; ++tc) {           // tc: running tile count of this CTA
@@ -126,53 +128,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t tmem_d = tmem_base + acc * 2 * BN;
         const uint32_t tmem_s = tmem_d + BN;
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&conv[stage], phase);               // TMA landed and the A tile has been split
+          mbar_wait(&full[stage], phase);               // TMA bytes have landed
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(operands + stage * STAGE_BYTES);
           const uint64_t a_hi = make_smem_desc_sw128(sa);
           const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
           const uint64_t b_hi = make_smem_desc_sw128(sa + 2 * BLOCK_BYTES);
           const uint64_t b_lo = make_smem_desc_sw128(sa + 3 * BLOCK_BYTES);
-          if (!(p.dbg & 4))
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             const uint32_t first = (kb | k) ? 1u : 0u;
-            umma_ss<true>(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
-            umma_ss<true>(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_ss<true>(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+            umma_ss<false>(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
+            umma_ss<false>(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_ss<false>(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
           }
           tcgen05_commit(&empty[stage]);
           if (kb == nkb - 1) tcgen05_commit(&tfull[acc]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
-    }
-  } else if (warp >= 2 + EPI_WARPS) {
-    // ---- converter warps: A tile fp32 -> tf32 hi (in place) + tf32 lo, element for element at the
-    // same (swizzled) offsets, then publish to the async proxy that tcgen05.mma reads through
-    const int cid = (warp - (2 + EPI_WARPS)) * 32 + lane;
-    int stage = 0; uint32_t phase = 0;
-    const int my_kblocks = ((nstrips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile * nkb;
-    for (int it = 0; it < my_kblocks; ++it) {
-      mbar_wait(&full[stage], phase);
-      float4* a = reinterpret_cast<float4*>(operands + stage * STAGE_BYTES);
-      float4* alo = a + BLOCK_BYTES / 16;
-      if (!(p.dbg & 2))
-#pragma unroll
-      for (int i = 0; i < BLOCK_BYTES / 16 / (32 * CONV_WARPS); ++i) {
-        const int e = cid + i * 32 * CONV_WARPS;
-        const float4 x = a[e];
-        float4 h, l;
-        h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
-        l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
-        l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
-        a[e] = h; alo[e] = l;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&conv[stage]);
-      if (++stage == STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     // ---- epilogue warps 2..9: TMEM -> smem transpose -> (+bias, +residual, relu) -> coalesced stores.
@@ -203,10 +178,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           float4 v;
-          v.x = __fadd_rn(__uint_as_float(r[j]), __uint_as_float(rs[j]));
-          v.y = __fadd_rn(__uint_as_float(r[j + 1]), __uint_as_float(rs[j + 1]));
-          v.z = __fadd_rn(__uint_as_float(r[j + 2]), __uint_as_float(rs[j + 2]));
-          v.w = __fadd_rn(__uint_as_float(r[j + 3]), __uint_as_float(rs[j + 3]));
+          v.x = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));
+          v.y = __fmaf_rn(__uint_as_float(rs[j + 1]), F16_LO_INV, __uint_as_float(r[j + 1]));
+          v.z = __fmaf_rn(__uint_as_float(rs[j + 2]), F16_LO_INV, __uint_as_float(r[j + 2]));
+          v.w = __fmaf_rn(__uint_as_float(rs[j + 3]), F16_LO_INV, __uint_as_float(r[j + 3]));
           *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
         }
         __syncwarp();
@@ -214,13 +189,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int gc = cr * BN + col0 + sub_c;          // first of this lane's 4 columns
         if (gc < p.N) {                                 // N % 4 == 0
           const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
-          float4 res[4];
-          if (p.residual) {
+          uint2 rh[4], rl[4];
+          if (p.res_hi) {
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
               const int gr = wrow0 + pass * 8 + sub_r;
-              res[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const float4*>(p.residual + (size_t)gr * p.N + gc))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+              const size_t o = (size_t)gr * p.N + gc;
+              rh[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_hi + o)) : make_uint2(0u, 0u);
+              rl[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_lo + o)) : make_uint2(0u, 0u);
             }
           }
 #pragma unroll
@@ -232,14 +208,23 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               v.x = __fadd_rn(v.x, b4.x); v.y = __fadd_rn(v.y, b4.y);
               v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
               const size_t o = (size_t)gr * p.N + gc;
-              if (p.residual) {
-                v.x = __fadd_rn(v.x, res[pass].x); v.y = __fadd_rn(v.y, res[pass].y);
-                v.z = __fadd_rn(v.z, res[pass].z); v.w = __fadd_rn(v.w, res[pass].w);
+              if (p.res_hi) {
+                const __half* h4 = reinterpret_cast<const __half*>(&rh[pass]);
+                const __half* l4 = reinterpret_cast<const __half*>(&rl[pass]);
+                v.x = __fadd_rn(v.x, join_f16(h4[0], l4[0])); v.y = __fadd_rn(v.y, join_f16(h4[1], l4[1]));
+                v.z = __fadd_rn(v.z, join_f16(h4[2], l4[2])); v.w = __fadd_rn(v.w, join_f16(h4[3], l4[3]));
               }
               if (p.relu) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               }
-              if (!(p.dbg & 1)) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+              if (p.out_hi) {
+                __half h4[4], l4[4];
+                split_f16(v.x, h4[0], l4[0]); split_f16(v.y, h4[1], l4[1]);
+                split_f16(v.z, h4[2], l4[2]); split_f16(v.w, h4[3], l4[3]);
+                *reinterpret_cast<uint2*>(p.out_hi + o) = *reinterpret_cast<uint2*>(h4);
+                *reinterpret_cast<uint2*>(p.out_lo + o) = *reinterpret_cast<uint2*>(l4);
+              }
             }
           }
         }
@@ -254,36 +239,46 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// fp32 [n] -> tf32 hi / lo
-__global__ void split_kernel(const float4* __restrict__ src, float4* __restrict__ hi,
-                             float4* __restrict__ lo, size_t n4) {
+// fp32 [n] -> fp16 pair
+__global__ void split_kernel(const float4* __restrict__ src, uint2* __restrict__ hi, uint2* __restrict__ lo,
+                             size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n4; i += stride) {
-    float4 x = __ldg(src + i), h, l;
-    h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
-    l.x = to_tf32_rna(__fsub_rn(x.x, h.x)); l.y = to_tf32_rna(__fsub_rn(x.y, h.y));
-    l.z = to_tf32_rna(__fsub_rn(x.z, h.z)); l.w = to_tf32_rna(__fsub_rn(x.w, h.w));
-    hi[i] = h; lo[i] = l;
+    const float4 x = __ldg(src + i);
+    __half h[4], l[4];
+    split_f16(x.x, h[0], l[0]); split_f16(x.y, h[1], l[1]);
+    split_f16(x.z, h[2], l[2]); split_f16(x.w, h[3], l[3]);
+    hi[i] = *reinterpret_cast<uint2*>(h);
+    lo[i] = *reinterpret_cast<uint2*>(l);
   }
 }
 
 // LayerNorm over the last dim (torch.nn.LayerNorm, eps inside the sqrt, biased variance), one warp
-// per row, row held in registers (W <= 1024).
+// per row, row held in registers (W <= 1024); fp16 pair in, fp16 pair out.
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, int rows, int W, const float* __restrict__ gamma,
-                 const float* __restrict__ beta, float eps, float* __restrict__ out) {
+layernorm_kernel(const __half* __restrict__ xh, const __half* __restrict__ xl, int rows, int W,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 __half* __restrict__ oh, __half* __restrict__ ol) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
-  const float* src = x + (size_t)row * W;
+  const size_t base = (size_t)row * W;
   float4 v[MAXV];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int c = (i * 32 + lane) * 4;
-    v[i] = (c < W) ? __ldg(reinterpret_cast<const float4*>(src + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < W) {
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(xh + base + c));
+      const uint2 l = __ldg(reinterpret_cast<const uint2*>(xl + base + c));
+      const __half* h4 = reinterpret_cast<const __half*>(&h);
+      const __half* l4 = reinterpret_cast<const __half*>(&l);
+      v[i] = make_float4(join_f16(h4[0], l4[0]), join_f16(h4[1], l4[1]), join_f16(h4[2], l4[2]),
+                         join_f16(h4[3], l4[3]));
+    }
     sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   sum = warp_reduce_sum(sum);
@@ -308,55 +303,60 @@ layernorm_kernel(const float* __restrict__ x, int rows, int W, const float* __re
       float4 y;
       y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
       y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      *reinterpret_cast<float4*>(out + (size_t)row * W + c) = y;
+      __half h4[4], l4[4];
+      split_f16(y.x, h4[0], l4[0]); split_f16(y.y, h4[1], l4[1]);
+      split_f16(y.z, h4[2], l4[2]); split_f16(y.w, h4[3], l4[3]);
+      *reinterpret_cast<uint2*>(oh + base + c) = *reinterpret_cast<uint2*>(h4);
+      *reinterpret_cast<uint2*>(ol + base + c) = *reinterpret_cast<uint2*>(l4);
     }
   }
 }
 
-int launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t stream) {
+struct Pair { __half* hi; __half* lo; };
+
+int launch_split(const float* src, Pair dst, size_t n, cudaStream_t stream) {
   SSLAM_LAUNCH(KK_SPLIT, stream,
                split_kernel<<<num_sms() * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                                    reinterpret_cast<float4*>(hi), reinterpret_cast<float4*>(lo), n / 4));
+                                                               reinterpret_cast<uint2*>(dst.hi),
+                                                               reinterpret_cast<uint2*>(dst.lo), n / 4));
   return SSLAM_OK;
 }
 
-int launch_gemm(const float* a, const float* w_hi, const float* w_lo, int rows, int N, int K,
-                const float* bias, const float* residual, int relu, float* out_f32, cudaStream_t stream) {
-  CUtensorMap ta, tb_hi, tb_lo;
+int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, Pair residual, int relu,
+                float* out_f32, Pair out, cudaStream_t stream) {
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
-  if ((rc = make_tensor_map_2d(&ta, a, rows, K, BM, BK, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&tb_hi, w_hi, N, K, BN, BK, 4))) return rc;
-  if ((rc = make_tensor_map_2d(&tb_lo, w_lo, N, K, BN, BK, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&ta_hi, a.hi, rows, K, BM, BK, 2))) return rc;
+  if ((rc = make_tensor_map_2d(&ta_lo, a.lo, rows, K, BM, BK, 2))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_hi, w.hi, N, K, BN, BK, 2))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_lo, w.lo, N, K, BN, BK, 2))) return rc;
   static std::atomic<bool> configured{false};
   if (!configured.load()) {
-    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SMEM_TOTAL));
     configured.store(true);
   }
   GemmParams gp;
-  gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.residual = residual; gp.relu = relu;
-  gp.out_f32 = out_f32;
-  static const int dbg = getenv("SSLAM_GEMM_DBG") ? atoi(getenv("SSLAM_GEMM_DBG")) : 0;
-  gp.dbg = dbg;
+  gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.res_hi = residual.hi; gp.res_lo = residual.lo;
+  gp.relu = relu; gp.out_f32 = out_f32; gp.out_hi = out.hi; gp.out_lo = out.lo;
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,
-               gemm_tf32x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta, tb_hi, tb_lo, gp));
+               gemm_f16x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
   return SSLAM_OK;
 }
 
-int launch_layernorm(const float* x, int rows, int W, const float* g, const float* b, float* out,
-                     cudaStream_t stream) {
+int launch_layernorm(Pair x, int rows, int W, const float* g, const float* b, Pair out, cudaStream_t stream) {
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   SSLAM_LAUNCH(KK_LAYERNORM, stream,
-               if (W <= 128) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out);
-               else if (W <= 384) layernorm_kernel<3><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out);
-               else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x, rows, W, g, b, 1e-5f, out));
+               if (W <= 128) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo);
+               else if (W <= 384) layernorm_kernel<3><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo);
+               else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo));
   return SSLAM_OK;
 }
 
-// packed weights: for each Linear, hi then lo copies of the [out, in] matrix
-size_t packed_floats(int C, int Hd, int D, int blocks) {
+// packed weights: for each Linear, the fp16 hi then lo copies of the [out, in] matrix
+size_t packed_halves(int C, int Hd, int D, int blocks) {
   return 2 * ((size_t)Hd * C + (size_t)blocks * 2 * Hd * Hd + (size_t)D * Hd);
 }
 
@@ -372,7 +372,7 @@ using namespace sslam;
 //   [2+8*blocks] output_proj.weight [D,Hd]   [3+8*blocks] output_proj.bias [D]
 extern "C" size_t sslam_refiner_packed_bytes(int C, int Hd, int D, int blocks) {
   if (C <= 0 || Hd <= 0 || D <= 0 || blocks < 0) return 0;
-  return packed_floats(C, Hd, D, blocks) * sizeof(float);
+  return packed_halves(C, Hd, D, blocks) * sizeof(__half) + 64 * 256;
 }
 
 extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int Hd, int D, int blocks,
@@ -381,15 +381,15 @@ extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   SSLAM_REQUIRE(params && packed, SSLAM_EINVAL, "refiner_pack: null pointer");
-  SSLAM_REQUIRE(C % 4 == 0 && Hd % 4 == 0 && D % 4 == 0, SSLAM_EUNSUPPORTED,
-                "refiner: dims must be multiples of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0, SSLAM_EUNSUPPORTED,
+                "refiner: C and hidden must be multiples of 8, D of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
   SSLAM_REQUIRE(packed_bytes >= sslam_refiner_packed_bytes(C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner_pack: packed buffer too small");
-  float* w = static_cast<float*>(packed);
+  char* w = static_cast<char*>(packed);
   auto pack = [&](const float* src, size_t n) -> int {
-    int r = launch_split(src, w, w + n, n, stream);
-    w += 2 * n;
-    return r;
+    Pair d{reinterpret_cast<__half*>(w), reinterpret_cast<__half*>(w + align_up(n * 2, 256))};
+    w += 2 * align_up(n * 2, 256);
+    return launch_split(src, d, n, stream);
   };
   if ((rc = pack(params[0], (size_t)Hd * C))) return rc;
   for (int b = 0; b < blocks; ++b) {
@@ -400,11 +400,11 @@ extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int
 }
 
 extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks) {
-  (void)blocks; (void)C;
+  (void)blocks;
   if (rows <= 0) return 0;
   const size_t r = (size_t)rows;
-  // h_a, h_b, t, u [r,Hd] fp32; raw [r,D]
-  return (4 * r * Hd + r * D) * sizeof(float) + 8 * 256;
+  // pairs (4 B/element): x [r,C]; h_a, h_b, t, u [r,Hd];  fp32 raw [r,D]
+  return (r * C + 4 * r * Hd + r * D) * 4 + 16 * 256;
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
@@ -417,36 +417,45 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   SSLAM_REQUIRE(rows >= 0, SSLAM_EINVAL, "refiner: negative rows");
   if (rows == 0) return SSLAM_OK;
   SSLAM_REQUIRE(params && packed && x && ws && (out_f32 || out_bf16), SSLAM_EINVAL, "refiner: null pointer");
-  SSLAM_REQUIRE(C % 4 == 0 && Hd % 4 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
-                "refiner: dims must be multiples of 4 and hidden <= 1024 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
+                "refiner: C and hidden must be multiples of 8 (hidden <= 1024), D of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
   SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
   SSLAM_REQUIRE(ws_bytes >= sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner: workspace %zu < %zu", ws_bytes, sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks));
   const size_t r = (size_t)rows;
   char* wp = static_cast<char*>(ws);
-  auto take = [&](size_t floats) { float* q = reinterpret_cast<float*>(wp); wp += align_up(floats * 4, 256); return q; };
-  float* h_a = take(r * Hd); float* h_b = take(r * Hd); float* t = take(r * Hd); float* u = take(r * Hd);
-  float* raw = take(r * D);
-  const float* pk = static_cast<const float*>(packed);
-  auto next_w = [&](size_t n, const float*& hi, const float*& lo) { hi = pk; lo = pk + n; pk += 2 * n; };
+  auto take_pair = [&](size_t n) {
+    Pair q{reinterpret_cast<__half*>(wp), reinterpret_cast<__half*>(wp + align_up(n * 2, 256))};
+    wp += 2 * align_up(n * 2, 256);
+    return q;
+  };
+  Pair xs = take_pair(r * C), h_a = take_pair(r * Hd), h_b = take_pair(r * Hd), t = take_pair(r * Hd),
+       u = take_pair(r * Hd);
+  float* raw = reinterpret_cast<float*>(wp);
+  const char* pk = static_cast<const char*>(packed);
+  auto next_w = [&](size_t n) {
+    Pair q{reinterpret_cast<__half*>(const_cast<char*>(pk)),
+           reinterpret_cast<__half*>(const_cast<char*>(pk) + align_up(n * 2, 256))};
+    pk += 2 * align_up(n * 2, 256);
+    return q;
+  };
+  const Pair none{nullptr, nullptr};
 
-  const float *w_hi, *w_lo;
-  next_w((size_t)Hd * C, w_hi, w_lo);                                     // descriptor_refiner.py:76
-  if ((rc = launch_gemm(x, w_hi, w_lo, rows, Hd, C, params[1], nullptr, 1, h_a, stream))) return rc;
-  float* h_cur = h_a;
-  float* h_nxt = h_b;
+  if ((rc = launch_split(x, xs, r * C, stream))) return rc;
+  Pair w = next_w((size_t)Hd * C);                                        // descriptor_refiner.py:76
+  if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], none, 1, nullptr, h_a, stream))) return rc;
+  Pair h_cur = h_a, h_nxt = h_b;
   for (int b = 0; b < blocks; ++b) {                                      // :79-80, :108-126
     const float* const* bp = params + 2 + 8 * b;
     if ((rc = launch_layernorm(h_cur, rows, Hd, bp[0], bp[1], t, stream))) return rc;
-    next_w((size_t)Hd * Hd, w_hi, w_lo);
-    if ((rc = launch_gemm(t, w_hi, w_lo, rows, Hd, Hd, bp[3], nullptr, 1, u, stream))) return rc;
+    w = next_w((size_t)Hd * Hd);
+    if ((rc = launch_gemm(t, w, rows, Hd, Hd, bp[3], none, 1, nullptr, u, stream))) return rc;
     if ((rc = launch_layernorm(u, rows, Hd, bp[4], bp[5], t, stream))) return rc;
-    next_w((size_t)Hd * Hd, w_hi, w_lo);
-    if ((rc = launch_gemm(t, w_hi, w_lo, rows, Hd, Hd, bp[7], h_cur, 1, h_nxt, stream))) return rc;   // + identity, ReLU
-    float* tmp = h_cur; h_cur = h_nxt; h_nxt = tmp;
+    w = next_w((size_t)Hd * Hd);
+    if ((rc = launch_gemm(t, w, rows, Hd, Hd, bp[7], h_cur, 1, nullptr, h_nxt, stream))) return rc;   // + identity, ReLU
+    Pair tmp = h_cur; h_cur = h_nxt; h_nxt = tmp;
   }
-  next_w((size_t)D * Hd, w_hi, w_lo);                                     // :83
-  if ((rc = launch_gemm(h_cur, w_hi, w_lo, rows, D, Hd, params[3 + 8 * blocks], nullptr, 0, raw, stream)))
-    return rc;
+  w = next_w((size_t)D * Hd);                                             // :83
+  if ((rc = launch_gemm(h_cur, w, rows, D, Hd, params[3 + 8 * blocks], none, 0, raw, none, stream))) return rc;
   return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
 }

@@ -28,5 +28,5 @@ tot = 0.0
 for k, (ms, n) in prof.items():
     print(f"{k:16s} {ms / 10:8.3f} ms/call  ({n // 10} launches)")
     tot += ms / 10
-g = prof["gemm_tf32x3"][0] / 10
+g = prof["gemm_f16x3"][0] / 10
 print(f"total {tot:.3f} ms; GEMMs {flops / g / 1e9:.1f} TFLOP/s algorithmic; {g / 6 * 1e3:.1f} us per GEMM")
