@@ -119,9 +119,12 @@ int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radius, float* 
  *   coords: 0 = keypoints are in patch units (drop-in);
  *           1 = keypoints are in pixel units and DinoBackbone.pixel_to_patch (:167-178,
  *               (p-8)/16) is applied first.
+ *   out may be NULL when the fp16 pair (out_hi, out_lo: [B,N,C] fp16 each, value = hi + lo*2^-11,
+ *   the operand format of sslam_refiner_forward_f32) is requested instead of / in addition to fp32.
  */
 int sslam_gather_bilinear_f32(const float* feat, const float* kpts, int B, int h, int w, int C,
-                              int N, int coords, float* out, void* stream);
+                              int N, int coords, float* out, void* out_hi, void* out_lo,
+                              void* stream);
 
 /* Row-wise L2 normalisation, the tail of DescriptorRefiner.forward
  * (models/descriptor_refiner.py:86): out = in / max(||in||_2, eps).
@@ -138,14 +141,18 @@ int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f3
  *            bias}, norm2.{weight,bias}, fc2.{weight,bias}; output_proj.{weight [D,Hd], bias}
  *   packed : device buffer of sslam_refiner_packed_bytes(), filled once per weight set by
  *            sslam_refiner_pack_weights() (tf32 hi/lo copies of the Linear weights)
- *   x [rows,C] fp32 -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16, unit L2 norm
- * C, Hd, D multiples of 4; Hd <= 1024; LayerNorm eps is torch's default 1e-5.
+ *   x [rows,C] fp32 (or NULL with the pair x_hi/x_lo [rows,C] fp16 from sslam_gather_bilinear_f32)
+ *   -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16, unit L2 norm
+ * Arithmetic: fp16 hi/lo pairs (22 significant bits), three kind::f16 MMAs per product, fp32
+ * accumulation; |activation| must stay below 65504.  C, Hd multiples of 8, D of 4; Hd <= 1024;
+ * LayerNorm eps is torch's default 1e-5.
  */
 size_t sslam_refiner_packed_bytes(int C, int Hd, int D, int blocks);
 int sslam_refiner_pack_weights(const float* const* params, int C, int Hd, int D, int blocks,
                                void* packed, size_t packed_bytes, void* stream);
 size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks);
 int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
+                              const void* x_hi, const void* x_lo,
                               int rows, int C, int Hd, int D, int blocks, float eps_norm,
                               float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
                               void* stream);

@@ -12,6 +12,7 @@
 // Each tap of a keypoint is one contiguous C*4-byte row of the NHWC map: a warp reads it with
 // 128-bit loads (C % 4 == 0) and writes the (B,N,C) output the same way.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -64,7 +65,8 @@ __device__ __forceinline__ float blend(float a, float b, float c, float d, const
 template <bool VEC4>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 gather_kernel(const float* __restrict__ feat, const float* __restrict__ kpts, int B, int H, int W,
-              int C, int N, int coords, float* __restrict__ out) {
+              int C, int N, int coords, float* __restrict__ out, __half* __restrict__ out_hi,
+              __half* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const long long kp = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (kp >= (long long)B * N) return;
@@ -85,7 +87,18 @@ gather_kernel(const float* __restrict__ feat, const float* __restrict__ kpts, in
       r.y = blend(v0.y, v1.y, v2.y, v3.y, t);
       r.z = blend(v0.z, v1.z, v2.z, v3.z, t);
       r.w = blend(v0.w, v1.w, v2.w, v3.w, t);
-      *reinterpret_cast<float4*>(o + c) = r;
+      if (out) *reinterpret_cast<float4*>(o + c) = r;
+      if (out_hi) {                                       // fp16 pair for the tensor-core refiner
+        __half h4[4], l4[4];
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h4[i] = __float2half_rn(rr[i]);
+          l4[i] = __float2half_rn(__fmul_rn(__fsub_rn(rr[i], __half2float(h4[i])), 2048.0f));
+        }
+        *reinterpret_cast<uint2*>(out_hi + (size_t)kp * C + c) = *reinterpret_cast<uint2*>(h4);
+        *reinterpret_cast<uint2*>(out_lo + (size_t)kp * C + c) = *reinterpret_cast<uint2*>(l4);
+      }
     }
   } else {
     for (int c = lane; c < C; c += 32) {
@@ -93,7 +106,13 @@ gather_kernel(const float* __restrict__ feat, const float* __restrict__ kpts, in
       float v1 = t.off[1] >= 0 ? __ldg(img + t.off[1] + c) : 0.f;
       float v2 = t.off[2] >= 0 ? __ldg(img + t.off[2] + c) : 0.f;
       float v3 = t.off[3] >= 0 ? __ldg(img + t.off[3] + c) : 0.f;
-      o[c] = blend(v0, v1, v2, v3, t);
+      const float r = blend(v0, v1, v2, v3, t);
+      if (out) o[c] = r;
+      if (out_hi) {
+        const __half h = __float2half_rn(r);
+        out_hi[(size_t)kp * C + c] = h;
+        out_lo[(size_t)kp * C + c] = __float2half_rn(__fmul_rn(__fsub_rn(r, __half2float(h)), 2048.0f));
+      }
     }
   }
 }
@@ -146,26 +165,31 @@ l2norm_kernel(const float* __restrict__ in, int rows, int D, float eps, float* _
 using namespace sslam;
 
 extern "C" int sslam_gather_bilinear_f32(const float* feat, const float* kpts, int B, int h, int w,
-                                         int C, int N, int coords, float* out, void* stream_) {
+                                         int C, int N, int coords, float* out, void* out_hi_, void* out_lo_,
+                                         void* stream_) {
+  __half* out_hi = static_cast<__half*>(out_hi_);
+  __half* out_lo = static_cast<__half*>(out_lo_);
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   SSLAM_REQUIRE(B >= 0 && h > 0 && w > 0 && C > 0 && N >= 0, SSLAM_EINVAL, "gather: bad size");
   SSLAM_REQUIRE(coords == 0 || coords == 1, SSLAM_EINVAL, "gather: coords must be 0 or 1");
   if (B == 0 || N == 0) return SSLAM_OK;
-  SSLAM_REQUIRE(feat && kpts && out, SSLAM_EINVAL, "gather: null pointer");
+  SSLAM_REQUIRE(feat && kpts && (out || (out_hi && out_lo)), SSLAM_EINVAL, "gather: null pointer");
+  SSLAM_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), SSLAM_EINVAL, "gather: pair outputs go together");
   SSLAM_REQUIRE((long long)h * w * C < (1ll << 31), SSLAM_EUNSUPPORTED, "gather: map too large");
   const long long total = (long long)B * N;
   const unsigned blocks = (unsigned)((total + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(feat) & 15) == 0) &&
-                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out_hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(out_lo) & 7) == 0);
   SSLAM_LAUNCH(KK_GATHER, stream,
                if (vec)
       gather_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
-                                                                      coords, out);
+                                                                      coords, out, out_hi, out_lo);
     else
       gather_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(feat, kpts, B, h, w, C, N,
-                                                                       coords, out));
+                                                                     coords, out, out_hi, out_lo));
   return SSLAM_OK;
 }
 

@@ -408,6 +408,7 @@ extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, 
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
+                                         const void* x_hi, const void* x_lo,
                                          int rows, int C, int Hd, int D, int blocks, float eps_norm,
                                          float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
                                          void* stream_) {
@@ -416,7 +417,8 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   cudaStream_t stream = (cudaStream_t)stream_;
   SSLAM_REQUIRE(rows >= 0, SSLAM_EINVAL, "refiner: negative rows");
   if (rows == 0) return SSLAM_OK;
-  SSLAM_REQUIRE(params && packed && x && ws && (out_f32 || out_bf16), SSLAM_EINVAL, "refiner: null pointer");
+  SSLAM_REQUIRE(params && packed && (x || (x_hi && x_lo)) && ws && (out_f32 || out_bf16), SSLAM_EINVAL,
+                "refiner: null pointer");
   SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
                 "refiner: C and hidden must be multiples of 8 (hidden <= 1024), D of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
   SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
@@ -441,7 +443,12 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   };
   const Pair none{nullptr, nullptr};
 
-  if ((rc = launch_split(x, xs, r * C, stream))) return rc;
+  if (x) {
+    if ((rc = launch_split(x, xs, r * C, stream))) return rc;
+  } else {                                                                // pair written by the gather kernel
+    xs.hi = static_cast<__half*>(const_cast<void*>(x_hi));
+    xs.lo = static_cast<__half*>(const_cast<void*>(x_lo));
+  }
   Pair w = next_w((size_t)Hd * C);                                        // descriptor_refiner.py:76
   if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], none, 1, nullptr, h_a, stream))) return rc;
   Pair h_cur = h_a, h_nxt = h_b;

@@ -24,13 +24,13 @@ SIGNATURES = {
                                       c_void_p]),
     "sslam_nms_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sslam_gather_bilinear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                                          c_int, c_void_p, c_void_p]),
+                                          c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sslam_l2norm_rows": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "sslam_refiner_packed_bytes": (c_size_t, [c_int] * 4),
     "sslam_refiner_pack_weights": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p,
                                            c_size_t, c_void_p]),
     "sslam_refiner_workspace_bytes": (c_size_t, [c_int] * 5),
-    "sslam_refiner_forward_f32": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int,
+    "sslam_refiner_forward_f32": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
                                           c_size_t, c_void_p]),
     "sslam_match_workspace_bytes": (c_size_t, [c_int] * 7),

@@ -105,8 +105,9 @@ def nms(saliency, radius):
     return out
 
 
-def gather_bilinear(features, keypoints, pixel_coords=False, out=None):
-    """features (B,h,w,C) fp32 NHWC, keypoints (B,N,2) fp32 -> (B,N,C) fp32."""
+def gather_bilinear(features, keypoints, pixel_coords=False, out=None, pair=False):
+    """features (B,h,w,C) fp32 NHWC, keypoints (B,N,2) fp32 -> (B,N,C) fp32.
+    pair=True returns instead the fp16 (hi, lo) pair consumed by refiner_forward (no fp32 copy)."""
     lib = _lib.load()
     _need_cuda(features, keypoints)
     feat = features.contiguous()
@@ -115,11 +116,16 @@ def gather_bilinear(features, keypoints, pixel_coords=False, out=None):
         raise RuntimeError("gather_bilinear expects fp32 tensors")
     B, h, w, C = feat.shape
     N = kp.shape[1]
-    if out is None:
+    hi = lo = None
+    if pair:
+        hi = torch.empty(B, N, C, dtype=torch.float16, device=feat.device)
+        lo = torch.empty(B, N, C, dtype=torch.float16, device=feat.device)
+    elif out is None:
         out = torch.empty(B, N, C, dtype=torch.float32, device=feat.device)
     _lib.check(lib.sslam_gather_bilinear_f32(_ptr(feat), _ptr(kp), B, h, w, C, N,
-                                             1 if pixel_coords else 0, _ptr(out), _stream()))
-    return out
+                                             1 if pixel_coords else 0, _ptr(out), _ptr(hi), _ptr(lo),
+                                             _stream()))
+    return (hi, lo) if pair else out
 
 
 def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False):
@@ -160,18 +166,31 @@ class RefinerPlan:
 
 
 def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None):
-    """x (..., C) fp32 -> unit-norm descriptors (rows, D) fp32 [and bf16 copy]."""
+    """x (..., C) fp32 — or the (hi, lo) fp16 pair from gather_bilinear(pair=True) —
+    -> unit-norm descriptors (rows, D) fp32 [and bf16 copy]."""
     lib = _lib.load()
-    _need_cuda(x)
-    xc = x.contiguous()
-    if xc.dtype != torch.float32 or xc.shape[-1] != plan.C:
-        raise RuntimeError("refiner_forward expects fp32 input with %d channels" % plan.C)
-    rows = xc.numel() // plan.C
-    out = torch.empty(rows, plan.D, dtype=torch.float32, device=xc.device)
-    out16 = torch.empty(rows, plan.D, dtype=torch.bfloat16, device=xc.device) if want_bf16 else None
+    x_hi = x_lo = None
+    if isinstance(x, (tuple, list)):
+        x_hi, x_lo = (t.contiguous() for t in x)
+        _need_cuda(x_hi, x_lo)
+        if x_hi.dtype != torch.float16 or x_lo.dtype != torch.float16 or x_hi.shape[-1] != plan.C:
+            raise RuntimeError("refiner_forward expects an fp16 (hi, lo) pair with %d channels" % plan.C)
+        xc, rows = None, x_hi.numel() // plan.C
+        ref = x_hi
+    else:
+        _need_cuda(x)
+        xc = x.contiguous()
+        if xc.dtype != torch.float32 or xc.shape[-1] != plan.C:
+            raise RuntimeError("refiner_forward expects fp32 input with %d channels" % plan.C)
+        rows = xc.numel() // plan.C
+        ref = xc
+    xc_dev = ref.device
+    out = torch.empty(rows, plan.D, dtype=torch.float32, device=xc_dev)
+    out16 = torch.empty(rows, plan.D, dtype=torch.bfloat16, device=xc_dev) if want_bf16 else None
     need = lib.sslam_refiner_workspace_bytes(rows, plan.C, plan.Hd, plan.D, plan.blocks)
-    ws = workspace if workspace is not None else _ws("refiner", need, xc.device)
-    _lib.check(lib.sslam_refiner_forward_f32(plan.ptrs, _ptr(plan.packed), _ptr(xc), rows, plan.C,
+    ws = workspace if workspace is not None else _ws("refiner", need, xc_dev)
+    _lib.check(lib.sslam_refiner_forward_f32(plan.ptrs, _ptr(plan.packed), _ptr(xc), _ptr(x_hi), _ptr(x_lo),
+                                             rows, plan.C,
                                              plan.Hd, plan.D, plan.blocks, float(eps), _ptr(out),
                                              _ptr(out16), _ptr(ws), ws.numel(), _stream()))
     return (out, out16) if want_bf16 else out

@@ -40,12 +40,14 @@ class FrontEnd:
         self._mark(timers, "begin")
         kp, sc, info = ops.decode_topk(saliency, self.K, self.r, self.pct)
         self._mark(timers, "decode")
-        sampled = ops.gather_bilinear(features, kp, pixel_coords=(self.grid == "pixel"))
+        fused = getattr(self.refiner, "mlp", "torch") == "tcgen05"
+        # the tensor-core refiner consumes fp16 (hi, lo) pairs: let the sampler write them directly
+        sampled = ops.gather_bilinear(features, kp, pixel_coords=(self.grid == "pixel"), pair=fused)
         self._mark(timers, "gather")
         B = kp.shape[0]
         res = dict(scores=sc, info=info)
         want16 = self.sim_mode == SIM_BF16
-        if getattr(self.refiner, "mlp", "torch") == "tcgen05":
+        if fused:
             out = self.refiner.forward_fused(sampled, want_bf16=want16)      # MLP + L2 norm, one call
             self._mark(timers, "refiner_mlp")
         else:
