@@ -17,7 +17,12 @@
 //     sslam_refiner_pack_weights.  Requires |activation| < 65504.
 //   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes the
 //     next layer's pair (or fp32 for the last layer) through a smem transpose, coalesced.
-//   * LayerNorm is a warp-per-row kernel, pair in, pair out.
+//   * LayerNorm never runs as a kernel.  For y = LN(h).W^T + c with LN(h) = (h - mu) * rho * g + b,
+//         y[r,n] = rho_r * ( (h.W'^T)[r,n] - mu_r * s1[n] ) + c0[n],
+//     W' = W * g (column scale), s1[n] = sum_k W'[n,k], c0[n] = sum_k b[k] W[n,k] + c[n]  (all folded
+//     once by sslam_refiner_pack_weights).  So the GEMM multiplies the *un-normalised* activations
+//     and its epilogue applies the two per-row scalars; those (mu_r, rho_r) are produced for free by
+//     the epilogue of the GEMM that wrote h (row sums of v and v^2 while storing).
 //
 // Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
 // inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
@@ -42,8 +47,9 @@ constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 
 constexpr int TP_LD = 20;                                // 16 columns + 4 pad (floats)
 constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
 constexpr int SMEM_TRANSP = EPI_WARPS * 32 * TP_LD * 4;
+constexpr int SMEM_STATS = 2 * 4 * 32 * 2 * 2 * 4;         // [parity][quarter][row][half][sum, sumsq]
 constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
-constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_BARS + 1024;
+constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS + SMEM_BARS + 1024;
 
 struct GemmParams {
   int rows, N, K;
@@ -54,6 +60,14 @@ struct GemmParams {
   float* out_f32;           // [rows, N] or null
   __half* out_hi;           // pair [rows, N] or null
   __half* out_lo;
+  // folded LayerNorm on the A operand (null = plain bias): per-row mean / rstd of A, per-column s1;
+  // `bias` then holds c0
+  const float* a_mean;
+  const float* a_rstd;
+  const float* s1;
+  // row statistics of the OUTPUT (after residual + ReLU) for the next folded LayerNorm, or null
+  float* out_mean;
+  float* out_rstd;
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -64,7 +78,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* operands = smem;
   float* transp = reinterpret_cast<float*>(smem + SMEM_OPERANDS);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
+  float* stats = reinterpret_cast<float*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -159,79 +174,128 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     float* tp = transp + ew * 32 * TP_LD;
     const int sub_r = lane >> 2;                        // store mapping: 4 lanes per row, 8 rows per pass
     const int sub_c = (lane & 3) * 4;
-    int tc = 0;
-    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x)
-    for (int ct = 0; ct < ntile; ++ct, ++tc) {
+    int tc = 0, sidx = 0;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x, ++sidx) {
       const int wrow0 = strip * BM + q * 32;            // first global row of this warp
-      const int acc = tc & 1;
-      mbar_wait(&tfull[acc], (tc >> 1) & 1);
-      tcgen05_fence_after();
-#pragma unroll 1
-      for (int un = 0; un < 4; ++un) {
-        const int col0 = half * 64 + un * 16;           // first column of this unit inside the tile
-        uint32_t r[16], rs[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0;
-        tmem_ld_32x16(taddr, r);
-        tmem_ld_32x16(taddr + BN, rs);
-        tmem_ld_wait();
-        __syncwarp();
+      float am[4], ar[4];                               // folded-LN scalars of this lane's 4 rows
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f}, rsq[4] = {0.f, 0.f, 0.f, 0.f};
+      if (p.a_mean) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 v;
-          v.x = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));
-          v.y = __fmaf_rn(__uint_as_float(rs[j + 1]), F16_LO_INV, __uint_as_float(r[j + 1]));
-          v.z = __fmaf_rn(__uint_as_float(rs[j + 2]), F16_LO_INV, __uint_as_float(r[j + 2]));
-          v.w = __fmaf_rn(__uint_as_float(rs[j + 3]), F16_LO_INV, __uint_as_float(r[j + 3]));
-          *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
+        for (int pass = 0; pass < 4; ++pass) {
+          const int gr = wrow0 + pass * 8 + sub_r;
+          am[pass] = gr < p.rows ? __ldg(p.a_mean + gr) : 0.f;
+          ar[pass] = gr < p.rows ? __ldg(p.a_rstd + gr) : 0.f;
         }
-        __syncwarp();
+      }
+      for (int ct = 0; ct < ntile; ++ct, ++tc) {
+        const int acc = tc & 1;
+        mbar_wait(&tfull[acc], (tc >> 1) & 1);
+        tcgen05_fence_after();
         int cr = ct + ct_rot; if (cr >= ntile) cr -= ntile;     // same rotation as the producer
-        const int gc = cr * BN + col0 + sub_c;          // first of this lane's 4 columns
-        if (gc < p.N) {                                 // N % 4 == 0
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
-          uint2 rh[4], rl[4];
-          if (p.res_hi) {
+#pragma unroll 1
+        for (int un = 0; un < 4; ++un) {
+          const int col0 = half * 64 + un * 16;         // first column of this unit inside the tile
+          uint32_t r[16], rs[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0;
+          tmem_ld_32x16(taddr, r);
+          tmem_ld_32x16(taddr + BN, rs);
+          tmem_ld_wait();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 v;
+            v.x = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));
+            v.y = __fmaf_rn(__uint_as_float(rs[j + 1]), F16_LO_INV, __uint_as_float(r[j + 1]));
+            v.z = __fmaf_rn(__uint_as_float(rs[j + 2]), F16_LO_INV, __uint_as_float(r[j + 2]));
+            v.w = __fmaf_rn(__uint_as_float(rs[j + 3]), F16_LO_INV, __uint_as_float(r[j + 3]));
+            *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
+          }
+          __syncwarp();
+          const int gc = cr * BN + col0 + sub_c;        // first of this lane's 4 columns
+          if (gc < p.N) {                               // N % 4 == 0
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.a_mean) s4 = __ldg(reinterpret_cast<const float4*>(p.s1 + gc));
+            uint2 rh[4], rl[4];
+            if (p.res_hi) {
+#pragma unroll
+              for (int pass = 0; pass < 4; ++pass) {
+                const int gr = wrow0 + pass * 8 + sub_r;
+                const size_t o = (size_t)gr * p.N + gc;
+                rh[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_hi + o)) : make_uint2(0u, 0u);
+                rl[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_lo + o)) : make_uint2(0u, 0u);
+              }
+            }
 #pragma unroll
             for (int pass = 0; pass < 4; ++pass) {
-              const int gr = wrow0 + pass * 8 + sub_r;
-              const size_t o = (size_t)gr * p.N + gc;
-              rh[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_hi + o)) : make_uint2(0u, 0u);
-              rl[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_lo + o)) : make_uint2(0u, 0u);
+              const int lr = pass * 8 + sub_r;
+              const int gr = wrow0 + lr;
+              if (gr < p.rows) {
+                float4 v = *reinterpret_cast<const float4*>(tp + lr * TP_LD + sub_c);
+                if (p.a_mean) {                         // rho * (acc - mu * s1) + c0
+                  const float nm = -am[pass], rr = ar[pass];
+                  v.x = __fmaf_rn(rr, __fmaf_rn(nm, s4.x, v.x), b4.x);
+                  v.y = __fmaf_rn(rr, __fmaf_rn(nm, s4.y, v.y), b4.y);
+                  v.z = __fmaf_rn(rr, __fmaf_rn(nm, s4.z, v.z), b4.z);
+                  v.w = __fmaf_rn(rr, __fmaf_rn(nm, s4.w, v.w), b4.w);
+                } else {
+                  v.x = __fadd_rn(v.x, b4.x); v.y = __fadd_rn(v.y, b4.y);
+                  v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
+                }
+                const size_t o = (size_t)gr * p.N + gc;
+                if (p.res_hi) {
+                  const __half* h4 = reinterpret_cast<const __half*>(&rh[pass]);
+                  const __half* l4 = reinterpret_cast<const __half*>(&rl[pass]);
+                  v.x = __fadd_rn(v.x, join_f16(h4[0], l4[0])); v.y = __fadd_rn(v.y, join_f16(h4[1], l4[1]));
+                  v.z = __fadd_rn(v.z, join_f16(h4[2], l4[2])); v.w = __fadd_rn(v.w, join_f16(h4[3], l4[3]));
+                }
+                if (p.relu) {
+                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                }
+                rsum[pass] += (v.x + v.y) + (v.z + v.w);
+                rsq[pass] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
+                if (p.out_hi) {
+                  __half h4[4], l4[4];
+                  split_f16(v.x, h4[0], l4[0]); split_f16(v.y, h4[1], l4[1]);
+                  split_f16(v.z, h4[2], l4[2]); split_f16(v.w, h4[3], l4[3]);
+                  *reinterpret_cast<uint2*>(p.out_hi + o) = *reinterpret_cast<uint2*>(h4);
+                  *reinterpret_cast<uint2*>(p.out_lo + o) = *reinterpret_cast<uint2*>(l4);
+                }
+              }
             }
           }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+      }
+      if (p.out_mean) {
+        // row statistics of what this strip stored: lanes sharing a row, then the two column halves
+        float* sc = stats + (sidx & 1) * (4 * 32 * 2 * 2);
 #pragma unroll
-          for (int pass = 0; pass < 4; ++pass) {
-            const int lr = pass * 8 + sub_r;
-            const int gr = wrow0 + lr;
-            if (gr < p.rows) {
-              float4 v = *reinterpret_cast<const float4*>(tp + lr * TP_LD + sub_c);
-              v.x = __fadd_rn(v.x, b4.x); v.y = __fadd_rn(v.y, b4.y);
-              v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
-              const size_t o = (size_t)gr * p.N + gc;
-              if (p.res_hi) {
-                const __half* h4 = reinterpret_cast<const __half*>(&rh[pass]);
-                const __half* l4 = reinterpret_cast<const __half*>(&rl[pass]);
-                v.x = __fadd_rn(v.x, join_f16(h4[0], l4[0])); v.y = __fadd_rn(v.y, join_f16(h4[1], l4[1]));
-                v.z = __fadd_rn(v.z, join_f16(h4[2], l4[2])); v.w = __fadd_rn(v.w, join_f16(h4[3], l4[3]));
-              }
-              if (p.relu) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              }
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
-              if (p.out_hi) {
-                __half h4[4], l4[4];
-                split_f16(v.x, h4[0], l4[0]); split_f16(v.y, h4[1], l4[1]);
-                split_f16(v.z, h4[2], l4[2]); split_f16(v.w, h4[3], l4[3]);
-                *reinterpret_cast<uint2*>(p.out_hi + o) = *reinterpret_cast<uint2*>(h4);
-                *reinterpret_cast<uint2*>(p.out_lo + o) = *reinterpret_cast<uint2*>(l4);
-              }
-            }
+        for (int pass = 0; pass < 4; ++pass) {
+          float a = rsum[pass], b = rsq[pass];
+          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
+          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
+          if ((lane & 3) == 0) {
+            float* e = sc + ((q * 32 + pass * 8 + sub_r) * 2 + half) * 2;
+            e[0] = a; e[1] = b;
+          }
+        }
+        named_bar_sync(1, 32 * EPI_WARPS);
+        if (half == 0) {
+          const int gr = wrow0 + lane;
+          if (gr < p.rows) {
+            const float* e = sc + (q * 32 + lane) * 4;
+            const float sm = e[0] + e[2], sq = e[1] + e[3];
+            const float mean = sm / (float)p.N;
+            const float var = fmaxf(sq / (float)p.N - mean * mean, 0.f);
+            p.out_mean[gr] = mean;
+            p.out_rstd[gr] = 1.0f / sqrtf(var + 1e-5f);
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
     }
   }
   tcgen05_fence_before();
@@ -254,62 +318,30 @@ __global__ void split_kernel(const float4* __restrict__ src, uint2* __restrict__
   }
 }
 
-// LayerNorm over the last dim (torch.nn.LayerNorm, eps inside the sqrt, biased variance), one warp
-// per row, row held in registers (W <= 1024); fp16 pair in, fp16 pair out.
-template <int MAXV>
-__global__ void __launch_bounds__(256)
-layernorm_kernel(const __half* __restrict__ xh, const __half* __restrict__ xl, int rows, int W,
-                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                 __half* __restrict__ oh, __half* __restrict__ ol) {
+// Weight folding for a Linear fed by LayerNorm(gamma, beta): one warp per output row n.
+//   W'[n,k] = W[n,k] * gamma[k]  -> fp16 pair;  s1[n] = sum_k W'[n,k] (of the pair actually used);
+//   c0[n] = sum_k beta[k] * W[n,k] + bias[n]
+__global__ void fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                               __half* __restrict__ hi, __half* __restrict__ lo, float* __restrict__ s1,
+                               float* __restrict__ c0) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const size_t base = (size_t)row * W;
-  float4 v[MAXV];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < W) {
-      const uint2 h = __ldg(reinterpret_cast<const uint2*>(xh + base + c));
-      const uint2 l = __ldg(reinterpret_cast<const uint2*>(xl + base + c));
-      const __half* h4 = reinterpret_cast<const __half*>(&h);
-      const __half* l4 = reinterpret_cast<const __half*>(&l);
-      v[i] = make_float4(join_f16(h4[0], l4[0]), join_f16(h4[1], l4[1]), join_f16(h4[2], l4[2]),
-                         join_f16(h4[3], l4[3]));
-    }
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float a = 0.f, c = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = W[(size_t)n * K + k];
+    const float wp = __fmul_rn(w, gamma[k]);
+    __half h, l;
+    split_f16(wp, h, l);
+    hi[(size_t)n * K + k] = h;
+    lo[(size_t)n * K + k] = l;
+    a += join_f16(h, l);
+    c = __fmaf_rn(beta[k], w, c);
   }
-  sum = warp_reduce_sum(sum);
-  const float mean = sum / (float)W;
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < W) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      sq += (a * a + b * b) + (cc * cc + d * d);
-    }
-  }
-  sq = warp_reduce_sum(sq);
-  const float rstd = 1.0f / sqrtf(sq / (float)W + eps);
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = (i * 32 + lane) * 4;
-    if (c < W) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
-      float4 y;
-      y.x = (v[i].x - mean) * rstd * g.x + b.x; y.y = (v[i].y - mean) * rstd * g.y + b.y;
-      y.z = (v[i].z - mean) * rstd * g.z + b.z; y.w = (v[i].w - mean) * rstd * g.w + b.w;
-      __half h4[4], l4[4];
-      split_f16(y.x, h4[0], l4[0]); split_f16(y.y, h4[1], l4[1]);
-      split_f16(y.z, h4[2], l4[2]); split_f16(y.w, h4[3], l4[3]);
-      *reinterpret_cast<uint2*>(oh + base + c) = *reinterpret_cast<uint2*>(h4);
-      *reinterpret_cast<uint2*>(ol + base + c) = *reinterpret_cast<uint2*>(l4);
-    }
-  }
+  a = warp_reduce_sum(a);
+  c = warp_reduce_sum(c);
+  if (lane == 0) { s1[n] = a; c0[n] = c + bias[n]; }
 }
 
 struct Pair { __half* hi; __half* lo; };
@@ -322,8 +354,10 @@ int launch_split(const float* src, Pair dst, size_t n, cudaStream_t stream) {
   return SSLAM_OK;
 }
 
-int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, Pair residual, int relu,
-                float* out_f32, Pair out, cudaStream_t stream) {
+struct RowStats { float* mean; float* rstd; };
+
+int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowStats a_ln, const float* s1,
+                Pair residual, int relu, float* out_f32, Pair out, RowStats out_stats, cudaStream_t stream) {
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_tensor_map_2d(&ta_hi, a.hi, rows, K, BM, BK, 2))) return rc;
@@ -339,6 +373,8 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, Pair 
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.res_hi = residual.hi; gp.res_lo = residual.lo;
   gp.relu = relu; gp.out_f32 = out_f32; gp.out_hi = out.hi; gp.out_lo = out.lo;
+  gp.a_mean = a_ln.mean; gp.a_rstd = a_ln.rstd; gp.s1 = s1;
+  gp.out_mean = out_stats.mean; gp.out_rstd = out_stats.rstd;
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,
@@ -346,18 +382,13 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, Pair 
   return SSLAM_OK;
 }
 
-int launch_layernorm(Pair x, int rows, int W, const float* g, const float* b, Pair out, cudaStream_t stream) {
-  const unsigned blocks = (unsigned)((rows + 7) / 8);
-  SSLAM_LAUNCH(KK_LAYERNORM, stream,
-               if (W <= 128) layernorm_kernel<1><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo);
-               else if (W <= 384) layernorm_kernel<3><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo);
-               else layernorm_kernel<8><<<blocks, 256, 0, stream>>>(x.hi, x.lo, rows, W, g, b, 1e-5f, out.hi, out.lo));
-  return SSLAM_OK;
-}
-
-// packed weights: for each Linear, the fp16 hi then lo copies of the [out, in] matrix
-size_t packed_halves(int C, int Hd, int D, int blocks) {
-  return 2 * ((size_t)Hd * C + (size_t)blocks * 2 * Hd * Hd + (size_t)D * Hd);
+// packed weights: per Linear the fp16 hi then lo copies of the [out, in] matrix; the LayerNorm-fed
+// ones (fc1, fc2 of every block) are stored folded and followed by s1[out], c0[out] (fp32)
+size_t pair_bytes(size_t n) { return 2 * align_up(n * 2, 256); }
+size_t vec_bytes(size_t n) { return 2 * align_up(n * 4, 256); }
+size_t packed_total(int C, int Hd, int D, int blocks) {
+  return pair_bytes((size_t)Hd * C) + (size_t)blocks * 2 * (pair_bytes((size_t)Hd * Hd) + vec_bytes(Hd)) +
+         pair_bytes((size_t)D * Hd);
 }
 
 }  // namespace
@@ -372,7 +403,7 @@ using namespace sslam;
 //   [2+8*blocks] output_proj.weight [D,Hd]   [3+8*blocks] output_proj.bias [D]
 extern "C" size_t sslam_refiner_packed_bytes(int C, int Hd, int D, int blocks) {
   if (C <= 0 || Hd <= 0 || D <= 0 || blocks < 0) return 0;
-  return packed_halves(C, Hd, D, blocks) * sizeof(__half) + 64 * 256;
+  return packed_total(C, Hd, D, blocks) + 256;
 }
 
 extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int Hd, int D, int blocks,
@@ -386,25 +417,33 @@ extern "C" int sslam_refiner_pack_weights(const float* const* params, int C, int
   SSLAM_REQUIRE(packed_bytes >= sslam_refiner_packed_bytes(C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner_pack: packed buffer too small");
   char* w = static_cast<char*>(packed);
-  auto pack = [&](const float* src, size_t n) -> int {
+  auto take_pair = [&](size_t n) {
     Pair d{reinterpret_cast<__half*>(w), reinterpret_cast<__half*>(w + align_up(n * 2, 256))};
-    w += 2 * align_up(n * 2, 256);
-    return launch_split(src, d, n, stream);
+    w += pair_bytes(n);
+    return d;
   };
-  if ((rc = pack(params[0], (size_t)Hd * C))) return rc;
+  if ((rc = launch_split(params[0], take_pair((size_t)Hd * C), (size_t)Hd * C, stream))) return rc;
   for (int b = 0; b < blocks; ++b) {
-    if ((rc = pack(params[2 + 8 * b + 2], (size_t)Hd * Hd))) return rc;
-    if ((rc = pack(params[2 + 8 * b + 6], (size_t)Hd * Hd))) return rc;
+    const float* const* bp = params + 2 + 8 * b;
+    for (int half = 0; half < 2; ++half) {                 // fc1 folded with norm1, fc2 with norm2
+      Pair d = take_pair((size_t)Hd * Hd);
+      float* s1 = reinterpret_cast<float*>(w);
+      float* c0 = reinterpret_cast<float*>(w + align_up((size_t)Hd * 4, 256));
+      w += vec_bytes(Hd);
+      SSLAM_LAUNCH(KK_SPLIT, stream,
+                   fold_ln_kernel<<<(Hd + 7) / 8, 256, 0, stream>>>(bp[4 * half + 2], bp[4 * half], bp[4 * half + 1],
+                                                                    bp[4 * half + 3], Hd, Hd, d.hi, d.lo, s1, c0));
+    }
   }
-  return pack(params[2 + 8 * blocks], (size_t)D * Hd);
+  return launch_split(params[2 + 8 * blocks], take_pair((size_t)D * Hd), (size_t)D * Hd, stream);
 }
 
 extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks) {
   (void)blocks;
   if (rows <= 0) return 0;
   const size_t r = (size_t)rows;
-  // pairs (4 B/element): x [r,C]; h_a, h_b, t, u [r,Hd];  fp32 raw [r,D]
-  return (r * C + 4 * r * Hd + r * D) * 4 + 16 * 256;
+  // pairs (4 B/element): x [r,C]; h_a, h_b, u [r,Hd];  fp32 raw [r,D];  6 row-stat vectors
+  return (r * C + 3 * r * Hd + r * D) * 4 + 6 * align_up(r * 4, 256) + 16 * 256;
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
@@ -421,27 +460,33 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
                 "refiner: null pointer");
   SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
                 "refiner: C and hidden must be multiples of 8 (hidden <= 1024), D of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
-  SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
+  SSLAM_REQUIRE(!x || (reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
   SSLAM_REQUIRE(ws_bytes >= sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner: workspace %zu < %zu", ws_bytes, sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks));
   const size_t r = (size_t)rows;
   char* wp = static_cast<char*>(ws);
   auto take_pair = [&](size_t n) {
     Pair q{reinterpret_cast<__half*>(wp), reinterpret_cast<__half*>(wp + align_up(n * 2, 256))};
-    wp += 2 * align_up(n * 2, 256);
+    wp += pair_bytes(n);
     return q;
   };
-  Pair xs = take_pair(r * C), h_a = take_pair(r * Hd), h_b = take_pair(r * Hd), t = take_pair(r * Hd),
-       u = take_pair(r * Hd);
+  auto take_stats = [&]() {
+    RowStats st{reinterpret_cast<float*>(wp), reinterpret_cast<float*>(wp + align_up(r * 4, 256))};
+    wp += 2 * align_up(r * 4, 256);
+    return st;
+  };
+  Pair xs = take_pair(r * C), h_a = take_pair(r * Hd), h_b = take_pair(r * Hd), u = take_pair(r * Hd);
+  RowStats st_a = take_stats(), st_b = take_stats(), st_u = take_stats();
   float* raw = reinterpret_cast<float*>(wp);
   const char* pk = static_cast<const char*>(packed);
   auto next_w = [&](size_t n) {
     Pair q{reinterpret_cast<__half*>(const_cast<char*>(pk)),
            reinterpret_cast<__half*>(const_cast<char*>(pk) + align_up(n * 2, 256))};
-    pk += 2 * align_up(n * 2, 256);
+    pk += pair_bytes(n);
     return q;
   };
   const Pair none{nullptr, nullptr};
+  const RowStats no_stats{nullptr, nullptr};
 
   if (x) {
     if ((rc = launch_split(x, xs, r * C, stream))) return rc;
@@ -450,19 +495,33 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
     xs.lo = static_cast<__half*>(const_cast<void*>(x_lo));
   }
   Pair w = next_w((size_t)Hd * C);                                        // descriptor_refiner.py:76
-  if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], none, 1, nullptr, h_a, stream))) return rc;
+  if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], no_stats, nullptr, none, 1, nullptr, h_a,
+                        blocks ? st_a : no_stats, stream)))
+    return rc;
   Pair h_cur = h_a, h_nxt = h_b;
+  RowStats st_cur = st_a, st_nxt = st_b;
   for (int b = 0; b < blocks; ++b) {                                      // :79-80, :108-126
-    const float* const* bp = params + 2 + 8 * b;
-    if ((rc = launch_layernorm(h_cur, rows, Hd, bp[0], bp[1], t, stream))) return rc;
+    // fc1( LN1(h) ) + ReLU, LayerNorm folded into the weights and the epilogue
     w = next_w((size_t)Hd * Hd);
-    if ((rc = launch_gemm(t, w, rows, Hd, Hd, bp[3], none, 1, nullptr, u, stream))) return rc;
-    if ((rc = launch_layernorm(u, rows, Hd, bp[4], bp[5], t, stream))) return rc;
+    const float* s1 = reinterpret_cast<const float*>(pk);
+    const float* c0 = reinterpret_cast<const float*>(pk + align_up((size_t)Hd * 4, 256));
+    pk += vec_bytes(Hd);
+    if ((rc = launch_gemm(h_cur, w, rows, Hd, Hd, c0, st_cur, s1, none, 1, nullptr, u, st_u, stream))) return rc;
+    // fc2( LN2(u) ) + identity, ReLU
     w = next_w((size_t)Hd * Hd);
-    if ((rc = launch_gemm(t, w, rows, Hd, Hd, bp[7], h_cur, 1, nullptr, h_nxt, stream))) return rc;   // + identity, ReLU
-    Pair tmp = h_cur; h_cur = h_nxt; h_nxt = tmp;
+    s1 = reinterpret_cast<const float*>(pk);
+    c0 = reinterpret_cast<const float*>(pk + align_up((size_t)Hd * 4, 256));
+    pk += vec_bytes(Hd);
+    const bool last = (b == blocks - 1);
+    if ((rc = launch_gemm(u, w, rows, Hd, Hd, c0, st_u, s1, h_cur, 1, nullptr, h_nxt, last ? no_stats : st_nxt,
+                          stream)))
+      return rc;
+    Pair tp = h_cur; h_cur = h_nxt; h_nxt = tp;
+    RowStats ts = st_cur; st_cur = st_nxt; st_nxt = ts;
   }
   w = next_w((size_t)D * Hd);                                             // :83
-  if ((rc = launch_gemm(h_cur, w, rows, D, Hd, params[3 + 8 * blocks], none, 0, raw, none, stream))) return rc;
+  if ((rc = launch_gemm(h_cur, w, rows, D, Hd, params[3 + 8 * blocks], no_stats, nullptr, none, 0, raw, none,
+                        no_stats, stream)))
+    return rc;
   return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
 }
