@@ -333,7 +333,7 @@ std::once_flag g_encode_once;
 
 namespace tc {
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                       uint32_t box_rows, uint32_t box_cols, int elem_bytes) {
+                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, bool swizzle128) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -349,7 +349,8 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   // 2-byte elements are moved as opaque 16-bit words (bf16 and fp16 alike)
   CUresult r = g_encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SSLAM_REQUIRE(r == CUDA_SUCCESS, SSLAM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return SSLAM_OK;

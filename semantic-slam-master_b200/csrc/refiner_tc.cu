@@ -15,8 +15,10 @@
 //     same HBM traffic as fp32) and are loaded by TMA straight into 128B-swizzled operand tiles —
 //     no conversion stage, no fp32 activations in HBM; weights are split once by
 //     sslam_refiner_pack_weights.  Requires |activation| < 65504.
-//   * the GEMM epilogue (thread = row, tcgen05.ld) fuses bias, residual add and ReLU and writes the
-//     next layer's pair (or fp32 for the last layer) through a smem transpose, coalesced.
+//   * the GEMM epilogue (thread = row, tcgen05.ld, 16 columns at a time) fuses bias / folded
+//     LayerNorm, residual add, ReLU and the row statistics, packs the next layer's pair (or fp32 for
+//     the last layer) into a dense shared-memory box and hands it to a TMA store, which also clips
+//     ragged rows / columns; no per-lane global stores.
 //   * LayerNorm never runs as a kernel.  For y = LN(h).W^T + c with LN(h) = (h - mu) * rho * g + b,
 //         y[r,n] = rho_r * ( (h.W'^T)[r,n] - mu_r * s1[n] ) + c0[n],
 //     W' = W * g (column scale), s1[n] = sum_k W'[n,k], c0[n] = sum_k b[k] W[n,k] + c[n]  (all folded
@@ -44,12 +46,15 @@ constexpr int STAGE_BYTES = 4 * BLOCK_BYTES;             // A_hi, A_lo, B_hi, B_
 constexpr int EPI_WARPS = 8;                             // two warps per TMEM lane quarter
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int TMEM_COLS = 512;                           // 2 x (128 main + 128 cross)
-constexpr int TP_LD = 20;                                // 16 columns + 4 pad (floats)
+constexpr int UNIT = 16;                                 // columns per epilogue step
+constexpr int STG_BYTES = 32 * UNIT * 4;                 // per warp: [32][16] fp16 hi | lo, or [32][16] fp32
 constexpr int SMEM_OPERANDS = STAGES * STAGE_BYTES;
-constexpr int SMEM_TRANSP = EPI_WARPS * 32 * TP_LD * 4;
+constexpr int SMEM_TRANSP = EPI_WARPS * STG_BYTES;
 constexpr int SMEM_STATS = 2 * 4 * 32 * 2 * 2 * 4;         // [parity][quarter][row][half][sum, sumsq]
+constexpr int MAX_N = 1024;
+constexpr int SMEM_VECS = 2 * MAX_N * 4;                 // bias / c0 and s1 of the layer, staged once per CTA
 constexpr int SMEM_BARS = (2 * STAGES + 4) * 8 + 16;
-constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS + SMEM_BARS + 1024;
+constexpr int SMEM_TOTAL = SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS + SMEM_VECS + SMEM_BARS + 1024;
 
 struct GemmParams {
   int rows, N, K;
@@ -74,13 +79,16 @@ struct GemmParams {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                  GemmParams p) {
+                  const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                  const __grid_constant__ CUtensorMap tmO_f32, GemmParams p) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* operands = smem;
-  float* transp = reinterpret_cast<float*>(smem + SMEM_OPERANDS);
+  unsigned char* staging = smem + SMEM_OPERANDS;
   float* stats = reinterpret_cast<float*>(smem + SMEM_OPERANDS + SMEM_TRANSP);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS);
+  float* sbias = reinterpret_cast<float*>(smem + SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS);
+  float* ss1 = sbias + MAX_N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMEM_OPERANDS + SMEM_TRANSP + SMEM_STATS + SMEM_VECS);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
@@ -103,6 +111,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {        // per-column vectors -> smem
+    sbias[i] = __ldg(p.bias + i);
+    ss1[i] = p.a_mean ? __ldg(p.s1 + i) : 0.f;
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -173,105 +185,111 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       }
     }
   } else {
-    // ---- epilogue warps 2..9: TMEM -> smem transpose -> (+bias, +residual, relu) -> coalesced stores.
-    // Warps w and w+4 share a TMEM lane quarter and each take half of the tile's 128 columns, in
-    // units of 16 columns.
+    // ---- epilogue warps 2..9.  Warps w and w+4 share a TMEM lane quarter and each take half of
+    // the tile's 128 columns, 16 at a time: thread = row, all arithmetic in registers, result rows
+    // packed into a dense [32][16] box in shared memory and written by TMA.
     const int q = warp & 3;
     const int ew = warp - 2;
     const int half = ew >> 2;                           // which 64 columns of the tile
-    float* tp = transp + ew * 32 * TP_LD;
-    const int sub_r = lane >> 2;                        // store mapping: 4 lanes per row, 8 rows per pass
-    const int sub_c = (lane & 3) * 4;
+    unsigned char* stg = staging + ew * STG_BYTES;
+    if (lane == 0) { prefetch_tensormap(&tmO_hi); prefetch_tensormap(&tmO_lo); prefetch_tensormap(&tmO_f32); }
     int tc = 0, sidx = 0;
     for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x, ++sidx) {
       const int wrow0 = strip * BM + q * 32;            // first global row of this warp
-      float am[4], ar[4];                               // folded-LN scalars of this lane's 4 rows
-      float rsum[4] = {0.f, 0.f, 0.f, 0.f}, rsq[4] = {0.f, 0.f, 0.f, 0.f};
-      if (p.a_mean) {
-#pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          const int gr = wrow0 + pass * 8 + sub_r;
-          am[pass] = gr < p.rows ? __ldg(p.a_mean + gr) : 0.f;
-          ar[pass] = gr < p.rows ? __ldg(p.a_rstd + gr) : 0.f;
+      const int grow = wrow0 + lane;                    // this thread's row
+      const bool row_ok = grow < p.rows;
+      float am = 0.f, ar = 0.f;                         // folded-LN scalars of this row
+      if (p.a_mean && row_ok) { am = __ldg(p.a_mean + grow); ar = __ldg(p.a_rstd + grow); }
+      float rsum = 0.f, rsq = 0.f;
+      // residual of one unit = this row's 16 values of each half of the pair; requested one unit
+      // ahead so that its HBM latency overlaps the arithmetic of the current unit
+      auto unit_col = [&](int ct_, int un_) {
+        int c = ct_ + ct_rot; if (c >= ntile) c -= ntile;
+        return c * BN + half * 64 + un_ * UNIT;
+      };
+      auto load_res = [&](int gc, uint4 (&h)[2], uint4 (&l)[2]) {
+        h[0] = h[1] = l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.res_hi && row_ok && gc < p.N) {
+          const size_t o = (size_t)grow * p.N + gc;
+          h[0] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o));
+          l[0] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o));
+          if (gc + 8 < p.N) {
+            h[1] = __ldg(reinterpret_cast<const uint4*>(p.res_hi + o + 8));
+            l[1] = __ldg(reinterpret_cast<const uint4*>(p.res_lo + o + 8));
+          }
         }
-      }
+      };
+      uint4 nh[2], nl[2];
+      load_res(unit_col(0, 0), nh, nl);
       for (int ct = 0; ct < ntile; ++ct, ++tc) {
         const int acc = tc & 1;
         mbar_wait(&tfull[acc], (tc >> 1) & 1);
         tcgen05_fence_after();
-        int cr = ct + ct_rot; if (cr >= ntile) cr -= ntile;     // same rotation as the producer
 #pragma unroll 1
-        for (int un = 0; un < 4; ++un) {
-          const int col0 = half * 64 + un * 16;         // first column of this unit inside the tile
-          uint32_t r[16], rs[16];
+        for (int un = 0; un < 64 / UNIT; ++un) {
+          const int col0 = half * 64 + un * UNIT;       // first column of this unit inside the tile
+          const int gc0 = unit_col(ct, un);             // ... and in the output (warp-uniform)
+          uint4 rh[2] = {nh[0], nh[1]}, rl[2] = {nl[0], nl[1]};
+          {
+            int nct = ct, nun = un + 1;
+            if (nun == 64 / UNIT) { nun = 0; ++nct; }
+            if (nct < ntile) load_res(unit_col(nct, nun), nh, nl);
+          }
+          if (gc0 >= p.N) continue;
+          uint32_t r[UNIT], rs[UNIT];
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0;
           tmem_ld_32x16(taddr, r);
           tmem_ld_32x16(taddr + BN, rs);
           tmem_ld_wait();
-          __syncwarp();
+          float v[UNIT];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 v;
-            v.x = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));
-            v.y = __fmaf_rn(__uint_as_float(rs[j + 1]), F16_LO_INV, __uint_as_float(r[j + 1]));
-            v.z = __fmaf_rn(__uint_as_float(rs[j + 2]), F16_LO_INV, __uint_as_float(r[j + 2]));
-            v.w = __fmaf_rn(__uint_as_float(rs[j + 3]), F16_LO_INV, __uint_as_float(r[j + 3]));
-            *reinterpret_cast<float4*>(tp + lane * TP_LD + j) = v;
+          for (int j = 0; j < UNIT; j += 4) {
+            const bool cok = gc0 + j < p.N;             // N % 4 == 0
+            const float4 b4 = *reinterpret_cast<const float4*>(sbias + gc0 + j);
+            const float4 s4 = *reinterpret_cast<const float4*>(ss1 + gc0 + j);
+            const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+            const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+            const __half* h8 = reinterpret_cast<const __half*>(&rh[j >> 3]) + (j & 7);
+            const __half* l8 = reinterpret_cast<const __half*>(&rl[j >> 3]) + (j & 7);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float x = __fmaf_rn(__uint_as_float(rs[j + e]), F16_LO_INV, __uint_as_float(r[j + e]));
+              if (p.a_mean) x = __fmaf_rn(ar, __fmaf_rn(-am, ss[e], x), bb[e]);   // rho*(acc - mu*s1) + c0
+              else x = __fadd_rn(x, bb[e]);
+              if (p.res_hi) x = __fadd_rn(x, join_f16(h8[e], l8[e]));
+              if (p.relu) x = fmaxf(x, 0.f);
+              if (!cok) x = 0.f;
+              v[j + e] = x;
+              rsum += x;
+              rsq = __fmaf_rn(x, x, rsq);
+            }
           }
+          // the previous TMA store of this warp must have finished reading the staging box
+          if (lane == 0) tma_store_wait_read<0>();
           __syncwarp();
-          const int gc = cr * BN + col0 + sub_c;        // first of this lane's 4 columns
-          if (gc < p.N) {                               // N % 4 == 0
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gc));
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.a_mean) s4 = __ldg(reinterpret_cast<const float4*>(p.s1 + gc));
-            uint2 rh[4], rl[4];
-            if (p.res_hi) {
+          if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(stg + lane * (UNIT * 4));
 #pragma unroll
-              for (int pass = 0; pass < 4; ++pass) {
-                const int gr = wrow0 + pass * 8 + sub_r;
-                const size_t o = (size_t)gr * p.N + gc;
-                rh[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_hi + o)) : make_uint2(0u, 0u);
-                rl[pass] = (gr < p.rows) ? __ldg(reinterpret_cast<const uint2*>(p.res_lo + o)) : make_uint2(0u, 0u);
-              }
-            }
+            for (int j = 0; j < UNIT; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            __half hh[UNIT], ll[UNIT];
 #pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int lr = pass * 8 + sub_r;
-              const int gr = wrow0 + lr;
-              if (gr < p.rows) {
-                float4 v = *reinterpret_cast<const float4*>(tp + lr * TP_LD + sub_c);
-                if (p.a_mean) {                         // rho * (acc - mu * s1) + c0
-                  const float nm = -am[pass], rr = ar[pass];
-                  v.x = __fmaf_rn(rr, __fmaf_rn(nm, s4.x, v.x), b4.x);
-                  v.y = __fmaf_rn(rr, __fmaf_rn(nm, s4.y, v.y), b4.y);
-                  v.z = __fmaf_rn(rr, __fmaf_rn(nm, s4.z, v.z), b4.z);
-                  v.w = __fmaf_rn(rr, __fmaf_rn(nm, s4.w, v.w), b4.w);
-                } else {
-                  v.x = __fadd_rn(v.x, b4.x); v.y = __fadd_rn(v.y, b4.y);
-                  v.z = __fadd_rn(v.z, b4.z); v.w = __fadd_rn(v.w, b4.w);
-                }
-                const size_t o = (size_t)gr * p.N + gc;
-                if (p.res_hi) {
-                  const __half* h4 = reinterpret_cast<const __half*>(&rh[pass]);
-                  const __half* l4 = reinterpret_cast<const __half*>(&rl[pass]);
-                  v.x = __fadd_rn(v.x, join_f16(h4[0], l4[0])); v.y = __fadd_rn(v.y, join_f16(h4[1], l4[1]));
-                  v.z = __fadd_rn(v.z, join_f16(h4[2], l4[2])); v.w = __fadd_rn(v.w, join_f16(h4[3], l4[3]));
-                }
-                if (p.relu) {
-                  v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                }
-                rsum[pass] += (v.x + v.y) + (v.z + v.w);
-                rsq[pass] += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + o) = v;
-                if (p.out_hi) {
-                  __half h4[4], l4[4];
-                  split_f16(v.x, h4[0], l4[0]); split_f16(v.y, h4[1], l4[1]);
-                  split_f16(v.z, h4[2], l4[2]); split_f16(v.w, h4[3], l4[3]);
-                  *reinterpret_cast<uint2*>(p.out_hi + o) = *reinterpret_cast<uint2*>(h4);
-                  *reinterpret_cast<uint2*>(p.out_lo + o) = *reinterpret_cast<uint2*>(l4);
-                }
-              }
+            for (int j = 0; j < UNIT; ++j) split_f16(v[j], hh[j], ll[j]);
+            uint4* dh = reinterpret_cast<uint4*>(stg + lane * (UNIT * 2));
+            uint4* dl = reinterpret_cast<uint4*>(stg + 32 * UNIT * 2 + lane * (UNIT * 2));
+            dh[0] = *reinterpret_cast<uint4*>(&hh[0]); dh[1] = *reinterpret_cast<uint4*>(&hh[8]);
+            dl[0] = *reinterpret_cast<uint4*>(&ll[0]); dl[1] = *reinterpret_cast<uint4*>(&ll[8]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.out_f32) {
+              tma_store_2d(&tmO_f32, stg, gc0, wrow0);
+            } else {
+              tma_store_2d(&tmO_hi, stg, gc0, wrow0);
+              tma_store_2d(&tmO_lo, stg + 32 * UNIT * 2, gc0, wrow0);
             }
+            tma_store_commit();
           }
         }
         tcgen05_fence_before();
@@ -279,32 +297,22 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
       if (p.out_mean) {
-        // row statistics of what this strip stored: lanes sharing a row, then the two column halves
+        // row statistics of what this strip stored: combine the two column halves of each row
         float* sc = stats + (sidx & 1) * (4 * 32 * 2 * 2);
-#pragma unroll
-        for (int pass = 0; pass < 4; ++pass) {
-          float a = rsum[pass], b = rsq[pass];
-          a += __shfl_xor_sync(0xffffffffu, a, 1); b += __shfl_xor_sync(0xffffffffu, b, 1);
-          a += __shfl_xor_sync(0xffffffffu, a, 2); b += __shfl_xor_sync(0xffffffffu, b, 2);
-          if ((lane & 3) == 0) {
-            float* e = sc + ((q * 32 + pass * 8 + sub_r) * 2 + half) * 2;
-            e[0] = a; e[1] = b;
-          }
-        }
+        float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
+        e[0] = rsum; e[1] = rsq;
         named_bar_sync(1, 32 * EPI_WARPS);
-        if (half == 0) {
-          const int gr = wrow0 + lane;
-          if (gr < p.rows) {
-            const float* e = sc + (q * 32 + lane) * 4;
-            const float sm = e[0] + e[2], sq = e[1] + e[3];
-            const float mean = sm / (float)p.N;
-            const float var = fmaxf(sq / (float)p.N - mean * mean, 0.f);
-            p.out_mean[gr] = mean;
-            p.out_rstd[gr] = 1.0f / sqrtf(var + 1e-5f);
-          }
+        if (half == 0 && row_ok) {
+          const float* f = sc + (q * 32 + lane) * 4;
+          const float sm = f[0] + f[2], sq = f[1] + f[3];
+          const float mean = sm / (float)p.N;
+          const float var = fmaxf(sq / (float)p.N - mean * mean, 0.f);
+          p.out_mean[grow] = mean;
+          p.out_rstd[grow] = 1.0f / sqrtf(var + 1e-5f);
         }
       }
     }
+    if (lane == 0) tma_store_wait_all<0>();             // all output boxes are in global memory
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -372,6 +380,16 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   if ((rc = make_tensor_map_2d(&ta_lo, a.lo, rows, K, BM, BK, 2))) return rc;
   if ((rc = make_tensor_map_2d(&tb_hi, w.hi, N, K, BN, BK, 2))) return rc;
   if ((rc = make_tensor_map_2d(&tb_lo, w.lo, N, K, BN, BK, 2))) return rc;
+  // outputs: dense [32 rows][16 cols] boxes, no swizzle; unused maps alias a valid one
+  CUtensorMap to_hi, to_lo, to_f32;
+  if (out.hi) {
+    if ((rc = make_tensor_map_2d(&to_hi, out.hi, rows, N, 32, UNIT, 2, false))) return rc;
+    if ((rc = make_tensor_map_2d(&to_lo, out.lo, rows, N, 32, UNIT, 2, false))) return rc;
+    to_f32 = to_hi;
+  } else {
+    if ((rc = make_tensor_map_2d(&to_f32, out_f32, rows, N, 32, UNIT, 4, false))) return rc;
+    to_hi = to_f32; to_lo = to_f32;
+  }
   static std::atomic<bool> configured{false};
   if (!configured.load()) {
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -388,7 +406,8 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,
-               gemm_f16x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, gp));
+               gemm_f16x3_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo,
+                                                                            to_f32, gp));
   return SSLAM_OK;
 }
 
@@ -468,8 +487,8 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   if (rows == 0) return SSLAM_OK;
   SSLAM_REQUIRE(params && packed && (x || (x_hi && x_lo)) && ws && (out_f32 || out_bf16), SSLAM_EINVAL,
                 "refiner: null pointer");
-  SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= 1024, SSLAM_EUNSUPPORTED,
-                "refiner: C and hidden must be multiples of 8 (hidden <= 1024), D of 4 (C=%d Hd=%d D=%d)", C, Hd, D);
+  SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= MAX_N && D <= MAX_N, SSLAM_EUNSUPPORTED,
+                "refiner: C and hidden must be multiples of 8, D of 4, hidden and D <= 1024 (C=%d Hd=%d D=%d)", C, Hd, D);
   SSLAM_REQUIRE(!x || (reinterpret_cast<uintptr_t>(x) & 15) == 0, SSLAM_EINVAL, "refiner: x must be 16-byte aligned");
   SSLAM_REQUIRE(ws_bytes >= sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks), SSLAM_EWORKSPACE,
                 "refiner: workspace %zu < %zu", ws_bytes, sslam_refiner_workspace_bytes(rows, C, Hd, D, blocks));

@@ -17,7 +17,7 @@ namespace tc {
 // Row-major 2-D tensor map [rows, cols] with a {box_cols, box_rows} box and 128-byte swizzle.
 // elem_bytes 4 (fp32/tf32) or 2 (bf16).  Returns SSLAM_OK or an error code.
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                       uint32_t box_rows, uint32_t box_cols, int elem_bytes);
+                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, bool swizzle128 = true);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------ device side
@@ -86,6 +86,25 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+
+// TMA store: shared (dense box) -> global (tensor map); completion tracked by bulk async-groups.
+// Out-of-range rows / columns of the box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the newest N groups have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // TMA prefetch of one box into L2 (no smem destination, no completion tracking)
