@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--cpu-sample-frames", type=int, default=33)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -226,9 +227,18 @@ def run_b200(a):
     sal, feat = synth.make_sequence(T, seq_id=rank, height=H, width=W, device=dev)
     in_bytes = sal.numel() * 4 + feat.numel() * 4
 
-    def step(timers=None):
-        feats, pairs, pscores, counts = fe.run_sequence(sal, feat, matchers.M1, chunk=a.chunk,
-                                                        timers=timers, ratio_thresh=0.8)
+    replay = None
+    if not a.no_graph:
+        replay, g_feats, g_pairs, g_pscores, g_counts = fe.capture_sequence(sal, feat, matchers.M1, chunk=a.chunk,
+                                                                            ratio_thresh=0.8)
+
+    def step(timers=None, eager=False):
+        if replay is not None and not eager:
+            replay()                                         # one graph launch = the whole step
+            pairs, pscores, counts = g_pairs, g_pscores, g_counts
+        else:
+            feats, pairs, pscores, counts = fe.run_sequence(sal, feat, matchers.M1, chunk=a.chunk,
+                                                            timers=timers, ratio_thresh=0.8)
         gathered = None
         if world > 1:
             gathered = sdist.gather_match_lists(pairs, pscores, counts, dst=0)
@@ -245,6 +255,13 @@ def run_b200(a):
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     launches0 = ops.launch_count()
+    launches_per_eager_step = None
+    if replay is not None:                                   # graph replays bypass the library's counter
+        c0 = ops.launch_count()
+        step(eager=True)
+        fence()
+        launches_per_eager_step = ops.launch_count() - c0
+        launches0 = ops.launch_count()
     timer_lists = []
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` sees only the timed steps
@@ -258,6 +275,8 @@ def run_b200(a):
     torch.cuda.profiler.stop()
     sampler.stop_flag = True
     launches = ops.launch_count() - launches0
+    if launches_per_eager_step is not None:
+        launches = launches_per_eager_step * a.steps         # kernels inside the replayed graphs
     ms_total = t_beg.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -271,13 +290,20 @@ def run_b200(a):
     # the library (sslam_profile_*), for the per-kernel roofline numbers
     ops.profile_enable(True)
     for _ in range(a.steps):
-        step()
+        step(eager=True)
     fence()
     kernel_ms = ops.profile_read()
     ops.profile_enable(False)
 
     # per-stage device time from the event marks (same stream as the kernels)
     stage_ms = {}
+    if replay is not None:                                   # stage marks need eager launches
+        timer_lists = []
+        for _ in range(a.steps):
+            tl = []
+            step(tl, eager=True)
+            timer_lists.append(tl)
+        fence()
     for tl in timer_lists:
         for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
             if n1 != "begin":
@@ -385,6 +411,7 @@ def run_b200(a):
             "data": "synthetic",
             "config": {"workload": workload_name(a), "frames_per_rank": T, "pairs_per_step": pairs_per_step,
                        "similarity_mode": mode_name, "chunk": a.chunk,
+                       "launch": "CUDA graph replay (one graph per step)" if replay is not None else "eager",
                        "l2_policy": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)",
                        "parallelism": f"{world} independent sequence shard(s), final NCCL gather of match lists"
                        if world > 1 else "single GPU"},

@@ -106,6 +106,28 @@ class FrontEnd:
         return feats, pairs, pscores, counts
 
     @torch.no_grad()
+    def capture_sequence(self, saliency, features, variant=matchers.M1, chunk=64, **kw):
+        """Capture run_sequence on the given (static) input tensors into a CUDA graph.
+
+        Every launch of the step (≈ 600 kernels of this library plus a few torch copies) is recorded
+        once; ``replay()`` re-issues them with one graph launch, which removes the per-launch host
+        cost (it matters when 8 ranks share the host cores).  New data is fed by copying into
+        ``saliency`` / ``features`` before ``replay()``; results land in the returned tensors.
+        Returns (replay, feats, pairs, pair_scores, counts)."""
+        # warm-up on a side stream (lazy initialisation, workspaces, packed weights)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.run_sequence(saliency, features, variant, chunk=chunk, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            feats, pairs, pscores, counts = self.run_sequence(saliency, features, variant, chunk=chunk, **kw)
+        return graph.replay, feats, pairs, pscores, counts
+
+    @torch.no_grad()
     def run_sequence_host(self, saliency_host, features_host, variant=matchers.M1, chunk=64,
                           out_host=None, **kw):
         """End-to-end entry point for HOST data: pinned (T,H,W,1) saliency and (T,h,w,C) features

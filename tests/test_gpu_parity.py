@@ -340,3 +340,27 @@ def test_abi_error_codes(dev):
     assert l.sslam_match_top2(p, 1, p, 1, z, 7, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1        # dtype
     assert l.sslam_launch_count() > 0
     torch.cuda.synchronize()
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    """FrontEnd.capture_sequence: a replayed CUDA graph of the whole step gives the eager results,
+    and follows new input data copied into the static buffers."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 128, 4).to(dev)
+    fe = FrontEnd(refiner, num_keypoints=256, grid="pixel")
+    salA, featA = synth.make_sequence(5, seq_id=3, height=96, width=128)
+    salB, featB = synth.make_sequence(5, seq_id=4, height=96, width=128)
+    sal, feat = salA.to(dev).clone(), featA.to(dev).clone()
+    replay, feats, pairs, pscores, counts = fe.capture_sequence(sal, feat, matchers.M1, chunk=2)
+    for s_src, f_src in ((salA, featA), (salB, featB), (salA, featA)):
+        sal.copy_(s_src.to(dev)); feat.copy_(f_src.to(dev))
+        replay()
+        torch.cuda.synchronize()
+        e_feats, e_pairs, e_pscores, e_counts = fe.run_sequence(s_src.to(dev), f_src.to(dev), matchers.M1, chunk=2)
+        assert torch.equal(feats["keypoints_pixel"], e_feats["keypoints_pixel"])
+        assert torch.equal(feats["descriptors"], e_feats["descriptors"])
+        assert torch.equal(counts, e_counts) and torch.equal(pairs, e_pairs)
+        assert torch.equal(pscores, e_pscores)
