@@ -202,3 +202,111 @@ def test_refiner_fused_vs_oracle_and_torch(dev):
     with torch.no_grad():
         out = m(cu(z["x"], dev)).cpu().numpy()
     assert np.abs(out - z["out"]).max() < 1e-5
+
+
+def test_gather_pair_output(dev):
+    """gather_bilinear(pair=True): fp16 (hi, lo) operands reproduce the fp32 sample to 22 bits."""
+    from sslam_b200 import ops
+    feat = cu(recipes.int_features(2, 30, 40, 384, 71), dev)
+    kp = cu(recipes.pixel_keypoints(2, 300, 480, 640, 72), dev)
+    ref = ops.gather_bilinear(feat, kp, pixel_coords=True)
+    hi, lo = ops.gather_bilinear(feat, kp, pixel_coords=True, pair=True)
+    assert hi.dtype == torch.float16 and lo.dtype == torch.float16 and hi.shape == ref.shape
+    rec = hi.float() + lo.float() / 2048.0
+    err = (rec - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -21 + 1e-7).all())
+
+
+def test_profile_api(dev):
+    from sslam_b200 import ops
+    ops.profile_enable(True)
+    x = torch.rand(3, 64, 96, device=dev)
+    ops.decode_topk(x, 20)
+    ops.l2norm_rows(torch.rand(10, 32, device=dev))
+    torch.cuda.synchronize()
+    prof = ops.profile_read()
+    ops.profile_enable(False)
+    assert prof["decode_scan"][1] == 1 and prof["decode_topk"][1] == 1 and prof["l2norm"][1] == 1
+    assert all(ms >= 0 for ms, _ in prof.values())
+    assert ops.profile_read() == {}
+
+
+def test_c3_bf16_pairs_with_ratio_rules(dev):
+    """c3-shaped: independent pairs, K=4096, bf16 similarity; M1 (ratio 0.8) and the rejecting M3
+    rule (0.9) against the fp32 oracle on the same descriptors: index agreement reported, scores
+    within 1e-3 relative."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, ops, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    sal, feat = synth.make_pairs(2)                       # (P, 2, ...)
+    fe = FrontEnd(refiner, num_keypoints=4096, grid="pixel", sim_mode=ops.SIM_BF16)
+    P = sal.shape[0]
+    f = fe.extract(sal.reshape(-1, *sal.shape[2:]).to(dev), feat.reshape(-1, *feat.shape[2:]).to(dev))
+    idx = torch.tensor([[2 * p, 2 * p + 1] for p in range(P)], dtype=torch.int32, device=dev)
+    pairs, sc, cnt = fe.match_pairs(f, idx, matchers.M3, ratio_threshold=0.9)
+    d = f["descriptors"].cpu().numpy()
+    for p in range(P):
+        ref, dist = oracle.match_m3(d[2 * p], d[2 * p + 1], 0.9)
+        got = pairs[p, :int(cnt[p])].cpu().numpy()
+        refset, gotset = {tuple(r) for r in ref.tolist()}, {tuple(r) for r in got.tolist()}
+        agree = len(refset & gotset) / max(len(refset | gotset), 1)
+        refd = {tuple(r): v for r, v in zip(ref.tolist(), dist.tolist())}
+        rel = max(abs((1 - sc[p, k].item()) - (1 - refd[tuple(r)])) / abs(1 - refd[tuple(r)])
+                  for k, r in enumerate(got.tolist()) if tuple(r) in refd)
+        print(f"c3 pair {p}: M3 {len(refset)} ref matches, index agreement {100 * agree:.2f}%, score rel err {rel:.1e}")
+        assert agree > 0.97 and rel < 1e-2
+
+
+def test_c4_all_pairs_keyframes(dev):
+    """c4-shaped: all unordered pairs of a keyframe set matched from one resident bank via
+    pair_index, matcher M2, dealt to 2 ranks block-cyclically; union equals the full list."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import dist as sdist, matchers, ops, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    KF, K = 6, 512
+    sal, feat = synth.make_sequence(KF, seq_id=5, stride=8)
+    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel", sim_mode=ops.SIM_F16X3)
+    f = fe.extract(sal.to(dev), feat.to(dev))
+    idx = sdist.all_pairs_index(KF)
+    assert idx.shape[0] == KF * (KF - 1) // 2
+    full = fe.match_pairs(f, idx.to(dev), matchers.M2)
+    d, s = f["descriptors"].cpu().numpy(), f["scores"].cpu().numpy()
+    exc = 0
+    for p, (a, b) in enumerate(idx.tolist()):
+        S = d[a].astype(np.float64) @ d[b].astype(np.float64).T
+        rm, rq = oracle.match_m2(d[a], d[b], s[a], s[b])
+        exc += compare_matches(S, rm, full[0][p, :int(full[2][p])].cpu().numpy(),
+                               threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
+    owned = [sdist.deal_pairs_block_cyclic(idx, 2, r, block=2) for r in range(2)]
+    assert torch.equal(torch.cat(owned).sort().values, torch.arange(idx.shape[0]))
+    for r in range(2):
+        part = fe.match_pairs(f, idx[owned[r]].to(dev), matchers.M2)
+        assert torch.equal(part[2], full[2][owned[r].to(dev)])
+        assert torch.equal(part[0], full[0][owned[r].to(dev)])
+    print("c4 near-tie exceptions:", exc)
+
+
+def test_c5_hires_pair(dev):
+    """c5-shaped: 1280x960 frames, K=8192, D=256, fp32 (f16x3) mode, one consecutive pair."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, ops, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 256, 4).to(dev)
+    sal, feat = synth.make_sequence(2, seq_id=6, height=960, width=1280)
+    K = 8192
+    fe = FrontEnd(refiner, num_keypoints=K, grid="pixel", sim_mode=ops.SIM_F16X3)
+    feats, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1)
+    okp, osc, oinfo = oracle.select_keypoints(sal.numpy(), K)
+    assert np.array_equal(feats["keypoints_pixel"].cpu().numpy(), okp)
+    d = feats["descriptors"].cpu().numpy()
+    S = d[0].astype(np.float64) @ d[1].astype(np.float64).T
+    ref = oracle.match_m1(d[0], d[1], 0.8)
+    exc = compare_matches(S, np.array([(i, j) for i, j, _ in ref]).reshape(-1, 2),
+                          pairs[0, :int(counts[0])].cpu().numpy())
+    assert int(counts[0]) > K // 4
+    print(f"c5: {int(counts[0])} matches, near-tie exceptions {exc}")
