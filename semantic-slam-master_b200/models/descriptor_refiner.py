@@ -74,9 +74,10 @@ class DescriptorRefiner(nn.Module):
             self._plan_key = key
         return self._plan_obj
 
-    def forward_fused(self, dino_features: torch.Tensor, want_bf16: bool = False):
-        """(..., C) -> (rows, D) unit-norm fp32 [, bf16 copy] through sslam_refiner_forward_f32."""
-        return ops.refiner_forward(self._plan(), dino_features, want_bf16=want_bf16)
+    def forward_fused(self, dino_features, want_bf16: bool = False, out=None, out16=None):
+        """(..., C) fp32 — or the fp16 (hi, lo) pair of ops.gather_bilinear(pair=True) —
+        -> (rows, D) unit-norm fp32 [, bf16 copy] through sslam_refiner_forward_f32."""
+        return ops.refiner_forward(self._plan(), dino_features, want_bf16=want_bf16, out=out, out16=out16)
 
     def forward(self, dino_features: torch.Tensor) -> torch.Tensor:
         """(B, N, C) features at keypoints -> (B, N, output_dim) unit-norm descriptors."""

@@ -165,7 +165,7 @@ class RefinerPlan:
                                                   _ptr(self.packed), nbytes, _stream()))
 
 
-def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None):
+def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=None, out16=None):
     """x (..., C) fp32 — or the (hi, lo) fp16 pair from gather_bilinear(pair=True) —
     -> unit-norm descriptors (rows, D) fp32 [and bf16 copy]."""
     lib = _lib.load()
@@ -185,8 +185,13 @@ def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None):
         rows = xc.numel() // plan.C
         ref = xc
     xc_dev = ref.device
-    out = torch.empty(rows, plan.D, dtype=torch.float32, device=xc_dev)
-    out16 = torch.empty(rows, plan.D, dtype=torch.bfloat16, device=xc_dev) if want_bf16 else None
+    if out is None:
+        out = torch.empty(rows, plan.D, dtype=torch.float32, device=xc_dev)
+    if want_bf16 and out16 is None:
+        out16 = torch.empty(rows, plan.D, dtype=torch.bfloat16, device=xc_dev)
+    for t in (out, out16):
+        if t is not None and (not t.is_contiguous() or t.numel() != rows * plan.D):
+            raise RuntimeError("refiner_forward: output buffers must be contiguous (rows, D)")
     need = lib.sslam_refiner_workspace_bytes(rows, plan.C, plan.Hd, plan.D, plan.blocks)
     ws = workspace if workspace is not None else _ws("refiner", need, xc_dev)
     _lib.check(lib.sslam_refiner_forward_f32(plan.ptrs, _ptr(plan.packed), _ptr(xc), _ptr(x_hi), _ptr(x_lo),

@@ -33,12 +33,15 @@ class FrontEnd:
             timers.append((name, ev))
 
     @torch.no_grad()
-    def extract(self, saliency, features, timers=None):
+    def extract(self, saliency, features, timers=None, out=None):
         """saliency (B,H,W,1)|(B,H,W), features (B,h,w,C) -> dict of device tensors:
         keypoints_pixel (B,K,2), scores (B,K), descriptors (B,K,D) [, descriptors_bf16], info.
-        `timers`, when a list, receives (stage, cuda event) marks on the current stream."""
+        `timers`, when a list, receives (stage, cuda event) marks on the current stream.
+        `out` (dict of preallocated slices: keypoints, scores, info, descriptors[, descriptors_bf16])
+        makes the kernels write into a resident bank instead of fresh tensors."""
         self._mark(timers, "begin")
-        kp, sc, info = ops.decode_topk(saliency, self.K, self.r, self.pct)
+        dec_out = (out["keypoints"], out["scores"], out["info"]) if out is not None else None
+        kp, sc, info = ops.decode_topk(saliency, self.K, self.r, self.pct, out=dec_out)
         self._mark(timers, "decode")
         fused = getattr(self.refiner, "mlp", "torch") == "tcgen05"
         # the tensor-core refiner consumes fp16 (hi, lo) pairs: let the sampler write them directly
@@ -47,14 +50,16 @@ class FrontEnd:
         B = kp.shape[0]
         res = dict(scores=sc, info=info)
         want16 = self.sim_mode == SIM_BF16
+        o32 = out["descriptors"] if out is not None else None
+        o16 = out.get("descriptors_bf16") if out is not None else None
         if fused:
-            out = self.refiner.forward_fused(sampled, want_bf16=want16)      # MLP + L2 norm, one call
+            res_d = self.refiner.forward_fused(sampled, want_bf16=want16, out=o32, out16=o16)   # MLP + L2 norm
             self._mark(timers, "refiner_mlp")
         else:
             raw = self.refiner.forward_unnormalized(sampled)
             self._mark(timers, "refiner_mlp")
-            out = ops.l2norm_rows(raw, want_bf16=want16)
-        d32, d16 = out if want16 else (out, None)
+            res_d = ops.l2norm_rows(raw, out=o32, out_bf16=o16, want_bf16=want16)
+        d32, d16 = res_d if want16 else (res_d, None)
         if want16:
             res["descriptors_bf16"] = d16.reshape(B, self.K, -1)
         self._mark(timers, "l2norm")
@@ -92,18 +97,29 @@ class FrontEnd:
         """Extract every frame once (in chunks) and match consecutive pairs.  Returns padded pair
         lists for the T-1 pairs, all on device."""
         T = saliency.shape[0]
-        descs, descs16, scores, kps = [], [], [], []
+        feats = self._alloc_bank(T, saliency.device)
         for s in range(0, T, chunk):
-            f = self.extract(saliency[s:s + chunk], features[s:s + chunk], timers=timers)
-            descs.append(f["descriptors"]); scores.append(f["scores"]); kps.append(f["keypoints_pixel"])
-            if self.sim_mode == SIM_BF16:
-                descs16.append(f["descriptors_bf16"])
-        feats = dict(descriptors=torch.cat(descs), scores=torch.cat(scores),
-                     keypoints_pixel=torch.cat(kps))
-        if descs16:
-            feats["descriptors_bf16"] = torch.cat(descs16)
+            e = min(T, s + chunk)
+            self.extract(saliency[s:e], features[s:e], timers=timers, out=self._bank_slice(feats, s, e))
+        if self.grid != "pixel":
+            feats["keypoints_pixel"] = feats["keypoints"] * self.patch + self.patch / 2
         pairs, pscores, counts = self.match_consecutive(feats, variant, timers=timers, **kw)
         return feats, pairs, pscores, counts
+
+    def _alloc_bank(self, T, device):
+        """Resident per-sequence bank the chunked extraction writes into (no concatenation)."""
+        D = self.refiner.output_dim
+        bank = dict(keypoints=torch.empty(T, self.K, 2, device=device),
+                    scores=torch.empty(T, self.K, device=device),
+                    info=torch.empty(T, 4, dtype=torch.int32, device=device),
+                    descriptors=torch.empty(T, self.K, D, device=device))
+        if self.sim_mode == SIM_BF16:
+            bank["descriptors_bf16"] = torch.empty(T, self.K, D, dtype=torch.bfloat16, device=device)
+        bank["keypoints_pixel"] = bank["keypoints"]     # pixel grid: the decode output is already pixels
+        return bank
+
+    def _bank_slice(self, bank, s, e):
+        return {k: v[s:e] for k, v in bank.items() if k != "keypoints_pixel"}
 
     @torch.no_grad()
     def capture_sequence(self, saliency, features, variant=matchers.M1, chunk=64, **kw):
@@ -148,7 +164,7 @@ class FrontEnd:
                                feat=[torch.empty((chunk,) + tuple(features_host.shape[1:]), device=dev) for _ in range(2)],
                                free=[torch.cuda.Event(), torch.cuda.Event()])
         st = self._stage
-        descs, descs16, scores, kps = [], [], [], []
+        feats = self._alloc_bank(T, dev)
         copy.wait_stream(compute)
         for ci, s in enumerate(range(0, T, chunk)):
             e = min(T, s + chunk)
@@ -161,15 +177,8 @@ class FrontEnd:
                 ready = torch.cuda.Event()
                 ready.record(copy)
             compute.wait_event(ready)
-            f = self.extract(st["sal"][b][:e - s], st["feat"][b][:e - s])
+            self.extract(st["sal"][b][:e - s], st["feat"][b][:e - s], out=self._bank_slice(feats, s, e))
             st["free"][b].record(compute)
-            descs.append(f["descriptors"]); scores.append(f["scores"]); kps.append(f["keypoints_pixel"])
-            if self.sim_mode == SIM_BF16:
-                descs16.append(f["descriptors_bf16"])
-        feats = dict(descriptors=torch.cat(descs), scores=torch.cat(scores),
-                     keypoints_pixel=torch.cat(kps))
-        if descs16:
-            feats["descriptors_bf16"] = torch.cat(descs16)
         pairs, pscores, counts = self.match_consecutive(feats, variant, **kw)
         if out_host is None:
             out_host = (torch.empty(pairs.shape, dtype=pairs.dtype, pin_memory=True),
