@@ -29,8 +29,6 @@
 // Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
 // inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
 // store epilogue of a strip overlaps the MMAs of the next.
-#include <stdlib.h>
-
 #include "tc_common.cuh"
 
 namespace sslam {
@@ -73,7 +71,6 @@ struct GemmParams {
   // row statistics of the OUTPUT (after residual + ReLU) for the next folded LayerNorm, or null
   float* out_mean;
   float* out_rstd;
-  int knobs;                // tuning knobs (SSLAM_GEMM_KNOBS): 1 = L2-prefetch the next strip's A tiles
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -127,13 +124,6 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       int stage = 0; uint32_t phase = 0;
       for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
         const int row0 = strip * BM;
-        if ((p.knobs & 1) && strip + (int)gridDim.x < nstrips) {
-          // the A tiles are first-touch HBM reads; pull the next strip into L2 while this one is multiplied
-          for (int kb = 0; kb < nkb; ++kb) {
-            tma_prefetch_l2_2d(&tmA_hi, kb * BK, (strip + (int)gridDim.x) * BM);
-            tma_prefetch_l2_2d(&tmA_lo, kb * BK, (strip + (int)gridDim.x) * BM);
-          }
-        }
         for (int ct = 0; ct < ntile; ++ct) {
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -401,8 +391,6 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   gp.relu = relu; gp.out_f32 = out_f32; gp.out_hi = out.hi; gp.out_lo = out.lo;
   gp.a_mean = a_ln.mean; gp.a_rstd = a_ln.rstd; gp.s1 = s1;
   gp.out_mean = out_stats.mean; gp.out_rstd = out_stats.rstd;
-  static const int knobs = getenv("SSLAM_GEMM_KNOBS") ? atoi(getenv("SSLAM_GEMM_KNOBS")) : 0;
-  gp.knobs = knobs;
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,
