@@ -37,9 +37,11 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 _REAL_STDOUT = None
-# dram__bytes_read.sum + dram__bytes_write.sum of one gemm_f16x3 launch (131072 x 384 x 384), from
-# the committed `ncu --set full` capture in profiles/ (None until re-captured for the current kernel)
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per gemm_f16x3 launch (131072 rows), averaged over the
+# six launches of one refiner call in the committed `ncu --set full` capture
+# (profiles/r1_all_kernels_full.txt: 3 x 362 MB plain, 2 x 582 MB with residual, 1 x 300 MB output
+# projection); the algorithmic figure for the same launches is 458 MB (pair in + pair out [+ residual]).
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 425e6
 
 
 def emit(line):

@@ -364,3 +364,43 @@ def test_cuda_graph_replay_matches_eager(dev):
         assert torch.equal(feats["descriptors"], e_feats["descriptors"])
         assert torch.equal(counts, e_counts) and torch.equal(pairs, e_pairs)
         assert torch.equal(pscores, e_pscores)
+
+
+def test_empty_and_degenerate_shapes(dev):
+    """Empty batches / zero keypoints / tiny maps go through the C ABI without launching."""
+    from sslam_b200 import ops
+    kp, sc, info = ops.decode_topk(torch.rand(0, 16, 16, device=dev), 8)
+    assert kp.shape == (0, 8, 2) and sc.shape == (0, 8)
+    kp, sc, info = ops.decode_topk(torch.rand(2, 16, 16, device=dev), 0)
+    assert kp.shape == (2, 0, 2)
+    out = ops.gather_bilinear(torch.rand(1, 4, 4, 8, device=dev), torch.zeros(1, 0, 2, device=dev))
+    assert out.shape == (1, 0, 8)
+    # 1x1 map: everything is the single pixel (reference: NMS keeps it, branch by threshold)
+    one = torch.full((1, 1, 1), 0.7, device=dev)
+    kp, sc, info = ops.decode_topk(one, 1)
+    okp, osc, oinfo = oracle.select_keypoints(one.cpu().numpy(), 1)
+    assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
+    assert int(info[0, 0]) == int(oinfo[0, 0])
+    # a map with rows shorter than a warp strip and K equal to the pixel count
+    m = cu(recipes.spread_saliency(5, 7, 91)[None], dev)
+    kp, sc, info = ops.decode_topk(m, 35)
+    okp, osc, oinfo = oracle.select_keypoints(m.cpu().numpy(), 35)
+    assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
+    with pytest.raises(RuntimeError):
+        ops.decode_topk(torch.rand(1, 8, 8), 4)                       # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        ops.match_top2(torch.rand(1, 4, 6, device=dev), torch.rand(1, 4, 6, device=dev))   # D % 4
+
+
+def test_decode_all_radii_and_percentiles(dev):
+    """Strip kernel (radius 1..3) and tiled kernel (radius 0, 4..8) against the oracle."""
+    from sslam_b200 import ops
+    sal = np.stack([recipes.spread_saliency(70, 150, 200 + i) for i in range(3)] +
+                   [recipes.box_saliency(70, 150, 210, quant=24)])
+    for r in (0, 1, 2, 3, 4, 6):
+        for pct in (0.5, 0.9, 0.25):
+            kp, sc, info = ops.decode_topk(cu(sal, dev), 60, nms_radius=r, min_score_percentile=pct)
+            okp, osc, oinfo = oracle.select_keypoints(sal, 60, r, pct)
+            assert np.array_equal(info.cpu().numpy()[:, 0], oinfo[:, 0]), (r, pct)
+            assert np.array_equal(kp.cpu().numpy(), okp), (r, pct)
+            assert np.array_equal(sc.cpu().numpy(), osc), (r, pct)
