@@ -36,6 +36,8 @@ namespace sslam {
 
 using namespace tc;
 
+long long* g_match_dbg = nullptr;   // set by sslam_debug_match_stalls (tools only, not part of the ABI)
+
 namespace {
 
 constexpr int BM = 128, BN = 128;
@@ -44,26 +46,14 @@ constexpr int NUM_THREADS = 192;
 constexpr int TP_LD = 36;                        // padded row length (floats) of the transpose tile
 
 template <int MODE> struct Cfg;
-template <> struct Cfg<SSLAM_SIM_BF16> {
-  static constexpr int TERMS = 1, STAGES = 6, BK = 64, ACC_COLS = BN, TMEM_COLS = 256;
-  static constexpr bool TF32 = false;
-  static constexpr uint32_t FMT = FMT_BF16;
-  static constexpr float CROSS_SCALE = 1.0f;
-};
 template <> struct Cfg<SSLAM_SIM_TF32X3> {
   static constexpr int TERMS = 2, STAGES = 3, BK = 32, ACC_COLS = 2 * BN, TMEM_COLS = 512;
   static constexpr bool TF32 = true;
   static constexpr uint32_t FMT = FMT_TF32;
   static constexpr float CROSS_SCALE = 1.0f;
 };
-template <> struct Cfg<SSLAM_SIM_F16X3> {            // hi/lo are fp16, lo carries a 2^11 scale
-  static constexpr int TERMS = 2, STAGES = 3, BK = 64, ACC_COLS = 2 * BN, TMEM_COLS = 512;
-  static constexpr bool TF32 = false;
-  static constexpr uint32_t FMT = FMT_F16;
-  static constexpr float CROSS_SCALE = 1.0f / 2048.0f;
-};
-
 struct TcParams {
+  long long* dbg;               // optional per-CTA stall counters of the MMA thread (debug aid), or null
   const int32_t* pair_index;
   int P, N, M, D;
   int32_t* nn12;
@@ -293,6 +283,334 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// A-resident variant (f16x3 and bf16: the 128-row strip of set 1 fits in shared memory).
+//
+// The streaming kernel above re-reads the A strip for every column tile, so each 128x128 tile pulls
+// 2 x TERMS x 16 KB per k-block through L2 — at 148 SMs that is the L2 slice throughput limit
+// (~42 B/cycle/SM measured), not the tensor pipe.  Here the strip is loaded once per work item and
+// stays in shared memory (per-k-block barriers, so the next item's strip streams in while the last
+// tile of the current item is still being multiplied); only B tiles stream, in 16 KB stages.
+// f16x3 issues two MMAs per k-step instead of three: B_hi and B_lo tiles are adjacent in the stage,
+// so  A_hi x [B_hi ; B_lo]  is ONE N=256 instruction writing hi.hi into TMEM columns [0,128) and
+// hi.lo into [128,256); A_lo x B_hi (N=128) then accumulates into [128,256).  Same tensor work, one
+// A_hi operand read less per step.  Eight epilogue warps (two per TMEM lane quarter, 64 columns each)
+// keep the epilogue under the MMA time of a tile.
+template <int MODE> struct RCfg;
+template <> struct RCfg<SSLAM_SIM_F16X3> {
+  static constexpr int TERMS = 2, B_BK = 32, B_SWZ = 64, B_STAGES = 4, ACC_COLS = 2 * BN, TMEM_COLS = 512;
+  static constexpr uint32_t FMT = FMT_F16;
+  static constexpr float CROSS_SCALE = 1.0f / 2048.0f;
+};
+template <> struct RCfg<SSLAM_SIM_BF16> {
+  static constexpr int TERMS = 1, B_BK = 64, B_SWZ = 128, B_STAGES = 6, ACC_COLS = BN, TMEM_COLS = 256;
+  static constexpr uint32_t FMT = FMT_BF16;
+  static constexpr float CROSS_SCALE = 1.0f;
+};
+constexpr int R_EPI_WARPS = 8;
+constexpr int R_THREADS = 64 + 32 * R_EPI_WARPS;
+constexpr int R_MAX_KB = 4;                      // D <= 256: four 64-element k-blocks of A
+constexpr int R_UNIT = 16;                       // columns per epilogue step
+
+template <int MODE>
+struct RSmem {
+  using C = RCfg<MODE>;
+  static constexpr int A_BYTES = R_MAX_KB * C::TERMS * BLOCK_BYTES;
+  static constexpr int B_TILE = BN * C::B_BK * 2;                    // one term of one stage
+  static constexpr int B_STAGE = C::TERMS * B_TILE;                  // hi then lo: a 256-row operand
+  static constexpr int OPERANDS = A_BYTES + C::B_STAGES * B_STAGE;
+  static constexpr int COLPART = 2 * 4 * BN * 8;                     // [acc][lane quarter][col] u64
+  static constexpr int TRANSP = R_EPI_WARPS * 32 * R_UNIT * 4;       // [warp][32 rows][16] fp32, swizzled
+  static constexpr int ROWMERGE = 2 * BM * 3 * 4;                    // [item parity][row][best, idx, second]
+  static constexpr int BARS = (2 * C::B_STAGES + 2 * R_MAX_KB + 4) * 8 + 16;
+  static constexpr int TOTAL = OPERANDS + COLPART + TRANSP + ROWMERGE + BARS + 1024;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(R_THREADS, 1)
+match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 TcParams p) {
+  using C = RCfg<MODE>;
+  using L = RSmem<MODE>;
+  constexpr int SUBS = 64 / C::B_BK;                                  // B stages per A k-block
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* a_res = smem;
+  unsigned char* b_stages = smem + L::A_BYTES;
+  u64* colpart = reinterpret_cast<u64*>(smem + L::OPERANDS);
+  float* transp = reinterpret_cast<float*>(smem + L::OPERANDS + L::COLPART);
+  float* rowmerge = reinterpret_cast<float*>(smem + L::OPERANDS + L::COLPART + L::TRANSP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::OPERANDS + L::COLPART + L::TRANSP + L::ROWMERGE);
+  uint64_t* full = bars;
+  uint64_t* empty = full + C::B_STAGES;
+  uint64_t* afull = empty + C::B_STAGES;
+  uint64_t* aempty = afull + R_MAX_KB;
+  uint64_t* tfull = aempty + R_MAX_KB;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int strips = (p.N + BM - 1) / BM;
+  const int nitems = strips * p.P;
+  const int ntile = (p.M + BN - 1) / BN;
+  const int nsub = (p.D + C::B_BK - 1) / C::B_BK;                     // B stages per tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int k = 0; k < R_MAX_KB; ++k) { mbar_init(&afull[k], 1); mbar_init(&aempty[k], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], R_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (elect_one()) {
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmB_hi);
+      if (C::TERMS == 2) { prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_lo); }
+      int stage = 0; uint32_t phase = 0;
+      int it = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        const int pair = item / strips;
+        int ia = pair, ib = pair;
+        if (p.pair_index) { ia = p.pair_index[2 * pair]; ib = p.pair_index[2 * pair + 1]; }
+        const int a_row = ia * p.N + (item - pair * strips) * BM;
+        const int b_row0 = ib * p.M;
+        for (int ct = 0; ct < ntile; ++ct) {
+          for (int sb = 0; sb < nsub; ++sb) {
+            if (ct == 0 && (sb % SUBS) == 0) {                  // this item's A k-block
+              const int kb = sb / SUBS;
+              mbar_wait(&aempty[kb], (uint32_t)(it & 1) ^ 1u);  // last tile of the previous item done with it
+              mbar_arrive_expect_tx(&afull[kb], C::TERMS * BLOCK_BYTES);
+              tma_load_2d(a_res + (kb * C::TERMS) * BLOCK_BYTES, &tmA_hi, &afull[kb], kb * 64, a_row);
+              if (C::TERMS == 2)
+                tma_load_2d(a_res + (kb * C::TERMS + 1) * BLOCK_BYTES, &tmA_lo, &afull[kb], kb * 64, a_row);
+            }
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* st = b_stages + stage * L::B_STAGE;
+            mbar_arrive_expect_tx(&full[stage], L::B_STAGE);
+            tma_load_2d(st, &tmB_hi, &full[stage], sb * C::B_BK, b_row0 + ct * BN);
+            if (C::TERMS == 2) tma_load_2d(st + L::B_TILE, &tmB_lo, &full[stage], sb * C::B_BK, b_row0 + ct * BN);
+            if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (elect_one()) {
+      const uint32_t idesc = make_instr_desc(C::FMT, BM, BN);
+      const uint32_t idesc_cat = make_instr_desc(C::FMT, BM, 2 * BN);
+      int stage = 0; uint32_t phase = 0;
+      int tc = 0, it = 0;
+      const bool dbg_on = p.dbg != nullptr;
+      long long w_full = 0, w_tempty = 0, w_afull = 0, t_begin = clock64(), tq = 0;
+      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+        for (int ct = 0; ct < ntile; ++ct, ++tc) {
+          const int acc = tc & 1;
+          if (dbg_on) tq = clock64();
+          mbar_wait(&tempty[acc], (((uint32_t)tc >> 1) & 1u) ^ 1u);
+          if (dbg_on) w_tempty += clock64() - tq;
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
+          for (int sb = 0; sb < nsub; ++sb) {
+            const int kb = sb / SUBS, h = sb % SUBS;
+            if (dbg_on) tq = clock64();
+            if (ct == 0 && h == 0) mbar_wait(&afull[kb], (uint32_t)(it & 1));
+            if (dbg_on) w_afull += clock64() - tq;
+            if (dbg_on) tq = clock64();
+            mbar_wait(&full[stage], phase);
+            if (dbg_on) w_full += clock64() - tq;
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(a_res + (kb * C::TERMS) * BLOCK_BYTES) + h * C::B_BK * 2;
+            const uint32_t sb_addr = smem_u32(b_stages + stage * L::B_STAGE);
+            const uint64_t a_hi = make_smem_desc_sw128(sa);
+            const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
+            const uint64_t b_cat = C::B_SWZ == 64 ? make_smem_desc_sw64(sb_addr) : make_smem_desc_sw128(sb_addr);
+#pragma unroll
+            for (int k = 0; k < C::B_BK / 16; ++k) {            // 16 elements = 32 bytes of K per instruction
+              const uint64_t adv = (uint64_t)(k * 32 >> 4);
+              const uint32_t first = (sb | k) ? 1u : 0u;
+              if (C::TERMS == 2) {
+                umma_ss<false>(tmem_d, a_hi + adv, b_cat + adv, idesc_cat, first);   // hi.hi | hi.lo
+                umma_ss<false>(tmem_d + BN, a_lo + adv, b_cat + adv, idesc, 1u);     // + lo.hi
+              } else {
+                umma_ss<false>(tmem_d, a_hi + adv, b_cat + adv, idesc, first);
+              }
+            }
+            tcgen05_commit(&empty[stage]);
+            if (ct == ntile - 1 && (h == SUBS - 1 || sb == nsub - 1)) tcgen05_commit(&aempty[kb]);
+            if (sb == nsub - 1) tcgen05_commit(&tfull[acc]);
+            if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + 4 * blockIdx.x;
+        d[0] = clock64() - t_begin; d[1] = w_full; d[2] = w_tempty; d[3] = w_afull;
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..9) ================================
+    const int q = warp & 3;                                     // TMEM lane quarter of this warp
+    const int ew = warp - 2;
+    const int half = ew >> 2;                                   // which 64 columns of every tile
+    const int et = threadIdx.x - 64;                            // 0..255
+    float* tp = transp + ew * 32 * R_UNIT;
+    const int sc = lane & 15, srh = lane >> 4;                  // column scan: column / row parity
+    const float NEG_INF = __int_as_float(0xff800000);
+    int tc = 0, it = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      const int pair = item / strips;
+      const int row0 = (item - pair * strips) * BM;
+      const int grow = row0 + q * 32 + lane;
+      const bool row_ok = grow < p.N;
+      int nvalid = p.N - (row0 + q * 32);
+      nvalid = nvalid < 0 ? 0 : (nvalid > 32 ? 32 : nvalid);
+      float best = NEG_INF, second = NEG_INF;
+      int bidx = 0x7fffffff;
+      for (int ct = 0; ct < ntile; ++ct, ++tc) {
+        const int acc = tc & 1;
+        mbar_wait(&tfull[acc], ((uint32_t)tc >> 1) & 1u);
+        tcgen05_fence_after();
+        u64* cp = colpart + (acc * 4 + q) * BN;
+        const int c0 = ct * BN;
+        // Units of 16 columns, software pipelined: the TMEM loads of unit u+1 are in flight while
+        // unit u is reduced.
+        //   row   : running (best, second) by value only — a pairwise max/min tree over the 16 new
+        //           values, three FMNMX per node; the index is looked up (first column equal to the
+        //           new maximum) only in the units that raise a row's maximum, which become rare
+        //           after the first tiles of an item;
+        //   column: the 32x16 chunk is transposed through shared memory (16-byte pieces XOR-swizzled
+        //           by row pair: the row-wise stores and the column-wise loads are both conflict
+        //           free); lane (c, parity) loads its 16 rows at once and reduces them as two
+        //           independent chains, the two parities are merged with one shuffle.
+        uint32_t r[R_UNIT], rs[R_UNIT];
+        {
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + half * 64;
+          tmem_ld_32x16(taddr, r);
+          if (C::TERMS == 2) tmem_ld_32x16(taddr + BN, rs);
+        }
+#pragma unroll
+        for (int un = 0; un < 64 / R_UNIT; ++un) {
+          const int col0 = half * 64 + un * R_UNIT;
+          const int gc0 = c0 + col0;
+          float v[R_UNIT];
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < R_UNIT; ++j)
+            v[j] = C::TERMS == 2 ? __fmaf_rn(__uint_as_float(rs[j]), C::CROSS_SCALE, __uint_as_float(r[j]))
+                                 : __uint_as_float(r[j]);
+          if (un + 1 < 64 / R_UNIT) {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + col0 + R_UNIT;
+            tmem_ld_32x16(taddr, r);
+            if (C::TERMS == 2) tmem_ld_32x16(taddr + BN, rs);
+          }
+          if (gc0 + R_UNIT > p.M) {                             // ragged last tile (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < R_UNIT; ++j)
+              if (gc0 + j >= p.M) v[j] = NEG_INF;               // never wins, never second
+          }
+          // ---- row top-2 (values), index on demand
+          {
+            float tb[R_UNIT / 2], ts[R_UNIT / 2];
+#pragma unroll
+            for (int j = 0; j < R_UNIT / 2; ++j) {
+              tb[j] = fmaxf(v[2 * j], v[2 * j + 1]);
+              ts[j] = fminf(v[2 * j], v[2 * j + 1]);
+            }
+#pragma unroll
+            for (int w = R_UNIT / 4; w >= 1; w >>= 1) {
+#pragma unroll
+              for (int j = 0; j < w; ++j) {
+                const float lo = fminf(tb[2 * j], tb[2 * j + 1]);
+                ts[j] = fmaxf(fmaxf(ts[2 * j], ts[2 * j + 1]), lo);
+                tb[j] = fmaxf(tb[2 * j], tb[2 * j + 1]);
+              }
+            }
+            const float ub = tb[0];
+            second = fmaxf(fmaxf(second, ts[0]), fminf(best, ub));
+            if (ub > best) {                                    // strict: an earlier column keeps ties
+              best = ub;
+              int f = R_UNIT - 1;
+#pragma unroll
+              for (int j = R_UNIT - 2; j >= 0; --j) f = (v[j] == ub) ? j : f;   // first column equal to ub
+              bidx = gc0 + f;
+            }
+          }
+          // ---- column argmax over the warp's 32 rows
+          if (nvalid < 32 && !row_ok) {
+#pragma unroll
+            for (int j = 0; j < R_UNIT; ++j) v[j] = NEG_INF;    // rows past N never win a column
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < R_UNIT / 4; ++j)
+            *reinterpret_cast<float4*>(tp + lane * R_UNIT + ((j ^ ((lane >> 1) & 3)) << 2)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          __syncwarp();
+          float cv[16];
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr)
+            cv[rr] = tp[(2 * rr + srh) * R_UNIT + ((((sc >> 2) ^ (rr & 3))) << 2) + (sc & 3)];
+          float m0 = cv[0], m1 = cv[8];
+          int r0 = 0, r1 = 8;
+#pragma unroll
+          for (int rr = 1; rr < 8; ++rr) {                      // rows ascending: lowest row wins ties
+            if (cv[rr] > m0) { m0 = cv[rr]; r0 = rr; }
+            if (cv[8 + rr] > m1) { m1 = cv[8 + rr]; r1 = 8 + rr; }
+          }
+          float cm = m0;
+          int cr = r0;
+          if (m1 > m0) { cm = m1; cr = r1; }
+          cr = 2 * cr + srh;
+          {
+            const float om = __shfl_xor_sync(0xffffffffu, cm, 16);
+            const int orow = __shfl_xor_sync(0xffffffffu, cr, 16);
+            if (om > cm || (om == cm && orow < cr)) { cm = om; cr = orow; }
+          }
+          if (srh == 0) cp[col0 + sc] = (nvalid > 0) ? pack_key(cm, (u32)(row0 + q * 32 + cr)) : 0ull;
+        }
+        // accumulator fully read: hand it back to the MMA warp
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        // merge the four lane quarters' column results and publish
+        named_bar_sync(1, 32 * R_EPI_WARPS);
+        if (et < BN) {
+          const u64* base = colpart + acc * 4 * BN;
+          u64 k = base[et];
+#pragma unroll
+          for (int w = 1; w < 4; ++w) { u64 o = base[w * BN + et]; k = o > k ? o : k; }
+          if (c0 + et < p.M && k) atomicMax(p.colkeys + (size_t)pair * p.M + c0 + et, k);
+        }
+      }
+      // merge the two column halves of every row (half 1 hands its state to half 0)
+      float* rm = rowmerge + (it & 1) * (BM * 3) + (q * 32 + lane) * 3;
+      if (half == 1) { rm[0] = best; rm[1] = __int_as_float(bidx); rm[2] = second; }
+      named_bar_sync(1, 32 * R_EPI_WARPS);
+      if (half == 0 && row_ok) {
+        const float ob = rm[0], os = rm[2];
+        const int oi = __float_as_int(rm[1]);
+        // second = second largest of the union, duplicates of the maximum count
+        const float lo_best = fminf(best, ob);
+        float sec = fmaxf(fmaxf(second, os), lo_best);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        const size_t o = (size_t)pair * p.N + grow;
+        p.nn12[o] = bidx; p.best12[o] = best; p.second12[o] = sec;
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
 // fp32 -> (tf32 hi, tf32 lo) split of a descriptor bank
 __global__ void split_tf32_kernel(const float4* __restrict__ src, float4* __restrict__ hi,
                                   float4* __restrict__ lo, size_t n4) {
@@ -333,7 +651,7 @@ std::once_flag g_encode_once;
 
 namespace tc {
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, bool swizzle128) {
+                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -349,7 +667,8 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
   // 2-byte elements are moved as opaque 16-bit words (bf16 and fp16 alike)
   CUresult r = g_encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                         2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                             : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SSLAM_REQUIRE(r == CUDA_SUCCESS, SSLAM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -406,10 +725,28 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   return SSLAM_OK;
 }
 
+template <int MODE>
+static int launch_res(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
+                      const CUtensorMap& b_lo, const TcParams& tp, cudaStream_t stream) {
+  using L = RSmem<MODE>;
+  static std::atomic<bool> configured{false};
+  if (!configured.load()) {
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(match_res_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          L::TOTAL));
+    configured.store(true);
+  }
+  const int items = ((tp.N + BM - 1) / BM) * tp.P;
+  const int grid = items < num_sms() ? items : num_sms();          // persistent: one CTA per SM
+  SSLAM_LAUNCH(KK_MATCH_TC, stream,
+               match_res_kernel<MODE><<<grid, R_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp));
+  return SSLAM_OK;
+}
+
 int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
                   int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                   u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream) {
   TcParams tp;
+  tp.dbg = g_match_dbg;
   tp.pair_index = pair_index; tp.P = P; tp.N = N; tp.M = M; tp.D = D;
   tp.nn12 = nn12; tp.best12 = best12; tp.second12 = second12; tp.colkeys = colkeys;
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
@@ -419,7 +756,7 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
     if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
     if ((rc = make_tensor_map_2d(&b_hi, bank2, (uint64_t)F2 * M, D, BN, 64, 2))) return rc;
     a_lo = a_hi; b_lo = b_hi;
-    return launch_tc<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
+    return launch_res<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
   // ---- split modes: the fp32 banks are split into hi / lo (tf32 pairs or fp16 pairs)
   const bool f16 = (dtype == SSLAM_SIM_F16X3);
@@ -461,13 +798,24 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
     if ((rc = split(f2, h2, l2, n2))) return rc;
   }
   const uint64_t rows2 = (uint64_t)F2 * M;
-  const uint32_t bk = f16 ? 64 : 32;
-  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, bk, (int)e))) return rc;
-  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, bk, (int)e))) return rc;
-  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, bk, (int)e))) return rc;
-  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, bk, (int)e))) return rc;
-  if (f16) return launch_tc<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
+  if (f16) {
+    // A strip resident (128-byte swizzled 64-element k-blocks), B streamed in 32-element / 64-byte
+    // swizzled stages
+    if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    return launch_res<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
+  }
+  if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, 32, 4))) return rc;
+  if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, 32, 4))) return rc;
   return launch_tc<SSLAM_SIM_TF32X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
 }
 
 }  // namespace sslam
+
+// Debug aid for tools/: per-CTA {total, wait_full, wait_tempty, wait_afull} cycle counters of the MMA
+// thread of match_res_kernel are written to buf (device, 4 * gridDim int64) while buf != NULL.
+extern "C" void sslam_debug_match_stalls(long long* buf) { sslam::g_match_dbg = buf; }

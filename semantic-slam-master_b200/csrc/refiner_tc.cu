@@ -35,6 +35,8 @@ namespace sslam {
 
 using namespace tc;
 
+long long* g_gemm_dbg = nullptr;    // set by sslam_debug_gemm_stalls (tools only, not part of the ABI)
+
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;               // BK fp16 = 128 bytes of K
@@ -63,15 +65,31 @@ struct GemmParams {
   float* out_f32;           // [rows, N] or null
   __half* out_hi;           // pair [rows, N] or null
   __half* out_lo;
-  // folded LayerNorm on the A operand (null = plain bias): per-row mean / rstd of A, per-column s1;
-  // `bias` then holds c0
-  const float* a_mean;
-  const float* a_rstd;
+  // folded LayerNorm on the A operand (null = plain bias): partial row sums / sums of squares of A
+  // ([a_parts][stat_stride], written by the GEMM that produced A), per-column s1; `bias` then holds c0
+  const float* a_sum;
+  const float* a_sq;
+  int a_parts;
   const float* s1;
-  // row statistics of the OUTPUT (after residual + ReLU) for the next folded LayerNorm, or null
-  float* out_mean;
-  float* out_rstd;
+  // partial row sums of the OUTPUT (after residual + ReLU) for the next folded LayerNorm, or null:
+  // part = column tile of the writer (pair kernel) or 0 (single-CTA kernel)
+  float* out_sum;
+  float* out_sq;
+  size_t stat_stride;
+  long long* dbg;           // optional per-CTA stall counters (debug aid), or null
 };
+
+// mean / rstd of row `grow` of the A operand from the producer's partial sums (fixed summation order)
+__device__ __forceinline__ void row_layernorm_scalars(const GemmParams& p, int grow, float& mean, float& rstd) {
+  float sm = 0.f, sq = 0.f;
+  for (int i = 0; i < p.a_parts; ++i) {
+    sm += __ldg(p.a_sum + (size_t)i * p.stat_stride + grow);
+    sq += __ldg(p.a_sq + (size_t)i * p.stat_stride + grow);
+  }
+  mean = sm / (float)p.K;
+  const float var = fmaxf(sq / (float)p.K - mean * mean, 0.f);
+  rstd = 1.0f / sqrtf(var + 1e-5f);
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -110,7 +128,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {        // per-column vectors -> smem
     sbias[i] = __ldg(p.bias + i);
-    ss1[i] = p.a_mean ? __ldg(p.s1 + i) : 0.f;
+    ss1[i] = p.a_sum ? __ldg(p.s1 + i) : 0.f;
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -144,6 +162,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   } else if (warp == 1) {
     if (elect_one()) {                                            // ---- MMA issuer
       const uint32_t idesc = make_instr_desc(FMT_F16, BM, BN);
+      const uint32_t idesc_cat = make_instr_desc(FMT_F16, BM, 2 * BN);
       int stage = 0; uint32_t phase = 0;
       const int my_tiles = ((nstrips - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * ntile;
       for (int tc = 0; tc < my_tiles; ++tc) {           // tc: running tile count of this CTA
@@ -159,14 +178,14 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
           const uint64_t a_hi = make_smem_desc_sw128(sa);
           const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
           const uint64_t b_hi = make_smem_desc_sw128(sa + 2 * BLOCK_BYTES);
-          const uint64_t b_lo = make_smem_desc_sw128(sa + 3 * BLOCK_BYTES);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             const uint32_t first = (kb | k) ? 1u : 0u;
-            umma_ss<false>(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
-            umma_ss<false>(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
-            umma_ss<false>(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+            // B_hi and B_lo tiles are adjacent: A_hi x [B_hi ; B_lo] is one N=256 instruction
+            // (hi.hi -> columns [0,128), hi.lo -> [128,256)); lo.hi then accumulates into the latter
+            umma_ss<false>(tmem_d, a_hi + adv, b_hi + adv, idesc_cat, first);
+            umma_ss<false>(tmem_s, a_lo + adv, b_hi + adv, idesc, 1u);
           }
           tcgen05_commit(&empty[stage]);
           if (kb == nkb - 1) tcgen05_commit(&tfull[acc]);
@@ -189,7 +208,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const int grow = wrow0 + lane;                    // this thread's row
       const bool row_ok = grow < p.rows;
       float am = 0.f, ar = 0.f;                         // folded-LN scalars of this row
-      if (p.a_mean && row_ok) { am = __ldg(p.a_mean + grow); ar = __ldg(p.a_rstd + grow); }
+      if (p.a_sum && row_ok) row_layernorm_scalars(p, grow, am, ar);
       float rsum = 0.f, rsq = 0.f;
       // residual of one unit = this row's 16 values of each half of the pair; requested one unit
       // ahead so that its HBM latency overlaps the arithmetic of the current unit
@@ -244,7 +263,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float x = __fmaf_rn(__uint_as_float(rs[j + e]), F16_LO_INV, __uint_as_float(r[j + e]));
-              if (p.a_mean) x = __fmaf_rn(ar, __fmaf_rn(-am, ss[e], x), bb[e]);   // rho*(acc - mu*s1) + c0
+              if (p.a_sum) x = __fmaf_rn(ar, __fmaf_rn(-am, ss[e], x), bb[e]);    // rho*(acc - mu*s1) + c0
               else x = __fadd_rn(x, bb[e]);
               if (p.res_hi) x = __fadd_rn(x, join_f16(h8[e], l8[e]));
               if (p.relu) x = fmaxf(x, 0.f);
@@ -286,19 +305,16 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
       }
-      if (p.out_mean) {
-        // row statistics of what this strip stored: combine the two column halves of each row
+      if (p.out_sum) {
+        // row sums of what this strip stored: combine the two column halves of each row
         float* sc = stats + (sidx & 1) * (4 * 32 * 2 * 2);
         float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
         e[0] = rsum; e[1] = rsq;
         named_bar_sync(1, 32 * EPI_WARPS);
         if (half == 0 && row_ok) {
           const float* f = sc + (q * 32 + lane) * 4;
-          const float sm = f[0] + f[2], sq = f[1] + f[3];
-          const float mean = sm / (float)p.N;
-          const float var = fmaxf(sq / (float)p.N - mean * mean, 0.f);
-          p.out_mean[grow] = mean;
-          p.out_rstd[grow] = 1.0f / sqrtf(var + 1e-5f);
+          p.out_sum[grow] = f[0] + f[2];
+          p.out_sq[grow] = f[1] + f[3];
         }
       }
     }
@@ -307,6 +323,330 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2), weight-stationary.  Used whenever K <= 384.
+//
+// The single-CTA kernel above streams both operands of every 128x128 tile through L2 and shared
+// memory (2 x 196 KB per tile at K = 384): at one CTA per SM that saturates the L2 slices and the
+// 128 B/cycle shared-memory port long before the tensor pipe.  Here two CTAs on the SMs of one TPC
+// share each MMA (M = 256: each CTA owns a 128-row strip and its accumulators; each holds HALF of the
+// weight tile), and a pair keeps its 128 weight columns resident for the whole launch:
+//   * grid = groups x ceil(N/128) pairs; pair (g, ct) keeps W[ct*128 .. +128, :] (64 rows per CTA,
+//     hi+lo, K/64 x 16 KB <= 96 KB) in shared memory and walks the 256-row strip pairs g, g+groups, ...
+//   * only activations stream: 32 KB per k-block and CTA, 3 stages; per tile a CTA pulls 196 KB
+//     instead of 393 KB through L2 and its MMAs read 6 KB instead of 8 KB of operands each;
+//   * the three pairs that own the column tiles of the same strips run in step, so a strip is
+//     fetched from DRAM once and served from L2 to the other two;
+//   * row statistics for the next folded LayerNorm are written as one partial (sum, sum of squares)
+//     per column tile and added up in a fixed order by the consumer (no atomics: results do not
+//     depend on scheduling).
+// Barriers: TMA of both CTAs signals the LEADER's `full` barriers (rank 0 issues every MMA);
+// tcgen05.commit multicasts `empty` / `tfull` to both CTAs; both epilogues arrive on the leader's
+// `tempty`.
+constexpr int P_STAGES = 3;
+constexpr int P_MAX_KB = 6;                               // K <= 384
+constexpr int B_HALF = 64 * 128;                          // 64 weight rows x 128 bytes of K
+constexpr int P_STAGE_BYTES = 2 * BLOCK_BYTES;            // A_hi, A_lo
+constexpr int P_SMEM_B = P_MAX_KB * 2 * B_HALF;
+constexpr int P_SMEM_A = P_STAGES * P_STAGE_BYTES;
+constexpr int P_SMEM_VECS = 2 * BN * 4;
+constexpr int P_SMEM_BARS = (2 * P_STAGES + 5) * 8 + 16;
+constexpr int P_SMEM_TOTAL = P_SMEM_B + P_SMEM_A + SMEM_TRANSP + SMEM_STATS + P_SMEM_VECS + P_SMEM_BARS + 1024;
+
+template <bool LN, bool RES, bool RELU, bool OUTF32, bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                 const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                 const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
+                 const __grid_constant__ CUtensorMap tmO_f32, GemmParams p, int groups) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* bres = smem;
+  unsigned char* a_stages = smem + P_SMEM_B;
+  unsigned char* staging = a_stages + P_SMEM_A;
+  float* stats = reinterpret_cast<float*>(staging + SMEM_TRANSP);
+  float* sbias = reinterpret_cast<float*>(staging + SMEM_TRANSP + SMEM_STATS);
+  float* ss1 = sbias + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + SMEM_TRANSP + SMEM_STATS + P_SMEM_VECS);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + P_STAGES;
+  uint64_t* bfull = bars + 2 * P_STAGES;
+  uint64_t* tfull = bfull + 1;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int ntile = (p.N + BN - 1) / BN;
+  const int pair_id = blockIdx.x >> 1;
+  const int ct = pair_id % ntile, g = pair_id / ntile;
+  const int col_base = ct * BN;
+  const int nsp = (p.rows + 2 * BM - 1) / (2 * BM);      // 256-row strip pairs
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(bfull, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < BN; i += NUM_THREADS) {          // this pair's 128 columns of the per-column vectors
+    const int c = col_base + i;
+    sbias[i] = c < p.N ? __ldg(p.bias + c) : 0.f;
+    ss1[i] = (LN && c < p.N) ? __ldg(p.s1 + c) : 0.f;
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {                                            // ---- TMA producer (both CTAs)
+      prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
+      prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
+      // resident weights: this CTA's 64 of the pair's 128 rows
+      const uint32_t bfull_leader = mapa_u32(smem_u32(bfull), 0);
+      if (rank == 0) mbar_arrive_expect_tx(bfull, 2u * (uint32_t)nkb * 2u * B_HALF);
+      for (int kb = 0; kb < nkb; ++kb) {
+        tma_load_2d_pair(bres + kb * 2 * B_HALF, &tmB_hi, bfull_leader, kb * BK, col_base + (int)rank * 64);
+        tma_load_2d_pair(bres + kb * 2 * B_HALF + B_HALF, &tmB_lo, bfull_leader, kb * BK, col_base + (int)rank * 64);
+      }
+      int stage = 0; uint32_t phase = 0;
+      for (int sp = g; sp < nsp; sp += groups) {
+        const int row0 = sp * 2 * BM + (int)rank * BM;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* st = a_stages + stage * P_STAGE_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+          if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * P_STAGE_BYTES);
+          tma_load_2d_pair(st, &tmA_hi, full_leader, kb * BK, row0);
+          tma_load_2d_pair(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {                               // ---- MMA issuer (leader CTA only)
+      const uint32_t idesc = make_instr_desc(FMT_F16, 2 * BM, BN);
+      int stage = 0; uint32_t phase = 0;
+      const bool dbg_on = p.dbg != nullptr;
+      long long w_full = 0, w_tempty = 0, tq = 0, t_begin = clock64();
+      mbar_wait(bfull, 0);
+      tcgen05_fence_after();
+      const long long w_b = clock64() - t_begin;
+      int tc = 0;
+      for (int sp = g; sp < nsp; sp += groups, ++tc) {
+        const int acc = tc & 1;
+        if (dbg_on) tq = clock64();
+        mbar_wait(&tempty[acc], (((uint32_t)tc >> 1) & 1u) ^ 1u);
+        if (dbg_on) w_tempty += clock64() - tq;
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+        const uint32_t tmem_s = tmem_d + BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          if (dbg_on) tq = clock64();
+          mbar_wait(&full[stage], phase);
+          if (dbg_on) w_full += clock64() - tq;
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(a_stages + stage * P_STAGE_BYTES);
+          const uint32_t sb = smem_u32(bres + kb * 2 * B_HALF);
+          const uint64_t a_hi = make_smem_desc_sw128(sa);
+          const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
+          const uint64_t b_hi = make_smem_desc_sw128(sb);
+          const uint64_t b_lo = make_smem_desc_sw128(sb + B_HALF);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            const uint32_t first = (kb | k) ? 1u : 0u;
+            umma_ss_pair(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
+            umma_ss_pair(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_ss_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+          }
+          tcgen05_commit_pair(&empty[stage], 3);
+          if (kb == nkb - 1) tcgen05_commit_pair(&tfull[acc], 3);
+          if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + 8 * blockIdx.x;
+        d[0] = clock64() - t_begin; d[1] = w_full; d[2] = w_tempty; d[3] = w_b;
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9 of both CTAs, each CTA on its own 128 rows.  The layer's options are
+    // template parameters: the per-element code has no branches on kernel arguments (the epilogue
+    // is instruction-issue bound — 8 warps share 4 schedulers with the two producer warps).
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    unsigned char* stg = staging + ew * STG_BYTES;
+    if (lane == 0) { prefetch_tensormap(&tmO_hi); prefetch_tensormap(&tmO_lo); prefetch_tensormap(&tmO_f32); }
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
+    const bool full_cols = col_base + BN <= p.N;          // no ragged columns in this pair's tile
+    int tc = 0;
+    for (int sp = g; sp < nsp; sp += groups, ++tc) {
+      const int wrow0 = sp * 2 * BM + (int)rank * BM + q * 32;
+      const int grow = wrow0 + lane;
+      const bool row_ok = grow < p.rows;
+      float am = 0.f, ar = 0.f, nam = 0.f;
+      if (LN && row_ok) { row_layernorm_scalars(p, grow, am, ar); nam = -am; }
+      float rsum = 0.f, rsq = 0.f;
+      // residual of one unit = this row's 16 values of each half of the pair, requested one unit ahead
+      const __half* res_h = RES ? p.res_hi + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
+      const __half* res_l = RES ? p.res_lo + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
+      auto load_res = [&](int gc, uint4 (&h)[2], uint4 (&l)[2]) {
+        if (gc + UNIT <= p.N) {
+          h[0] = __ldg(reinterpret_cast<const uint4*>(res_h + gc));
+          h[1] = __ldg(reinterpret_cast<const uint4*>(res_h + gc + 8));
+          l[0] = __ldg(reinterpret_cast<const uint4*>(res_l + gc));
+          l[1] = __ldg(reinterpret_cast<const uint4*>(res_l + gc + 8));
+        } else {
+          h[0] = h[1] = l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
+          if (gc < p.N) {
+            h[0] = __ldg(reinterpret_cast<const uint4*>(res_h + gc));
+            l[0] = __ldg(reinterpret_cast<const uint4*>(res_l + gc));
+          }
+        }
+      };
+      uint4 nh[2], nl[2];
+      if (RES) load_res(col_base + half * 64, nh, nl); // in flight while the accumulator completes
+      {
+        // pull what the NEXT strip pair of this warp will read row-wise (residual pair, LayerNorm
+        // partial sums) into L2 now, so that those loads are L2 hits when their turn comes
+        const int nrow = grow + groups * 2 * BM;
+        if (nrow < p.rows) {
+          if (RES) {
+            const size_t o = (size_t)nrow * p.N + col_base + half * 64;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_hi + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.res_lo + o));
+          }
+          if (LN && half == 0 && (lane & 7) == 0) {
+            for (int i = 0; i < p.a_parts; ++i) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a_sum + (size_t)i * p.stat_stride + nrow));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(p.a_sq + (size_t)i * p.stat_stride + nrow));
+            }
+          }
+        }
+      }
+      const int acc = tc & 1;
+      mbar_wait(&tfull[acc], ((uint32_t)tc >> 1) & 1u);
+      tcgen05_fence_after();
+      uint32_t r[UNIT], rs[UNIT];
+      {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + half * 64;
+        tmem_ld_32x16(taddr, r);
+        tmem_ld_32x16(taddr + BN, rs);
+      }
+#pragma unroll
+      for (int un = 0; un < 64 / UNIT; ++un) {
+        const int col0 = half * 64 + un * UNIT;         // first column of this unit inside the tile
+        const int gc0 = col_base + col0;                // ... and in the output (warp-uniform)
+        uint4 rh[2], rl[2];
+        if (RES) {
+          rh[0] = nh[0]; rh[1] = nh[1]; rl[0] = nl[0]; rl[1] = nl[1];
+          if (un + 1 < 64 / UNIT) load_res(gc0 + UNIT, nh, nl);
+        }
+        float v[UNIT];
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < UNIT; ++j) {
+          v[j] = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));   // fold the cross terms
+        }
+        if (un + 1 < 64 / UNIT) {                       // next unit's accumulators: in flight during the math
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + col0 + UNIT;
+          tmem_ld_32x16(taddr, r);
+          tmem_ld_32x16(taddr + BN, rs);
+        }
+        if (gc0 >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < UNIT; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + col0 + j);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          float ss[4] = {0.f, 0.f, 0.f, 0.f};
+          if (LN) {
+            const float4 s4 = *reinterpret_cast<const float4*>(ss1 + col0 + j);
+            ss[0] = s4.x; ss[1] = s4.y; ss[2] = s4.z; ss[3] = s4.w;
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = v[j + e];
+            if (LN) x = __fmaf_rn(ar, __fmaf_rn(nam, ss[e], x), bb[e]);         // rho*(acc - mu*s1) + c0
+            else x = __fadd_rn(x, bb[e]);
+            if (RES)
+              x = __fadd_rn(__fmaf_rn(__half2float(reinterpret_cast<const __half*>(rl)[j + e]), F16_LO_INV, x),
+                            __half2float(reinterpret_cast<const __half*>(rh)[j + e]));
+            if (RELU) x = fmaxf(x, 0.f);
+            v[j + e] = x;
+          }
+        }
+        if (!full_cols) {                               // ragged last column tile (warp-uniform)
+#pragma unroll
+          for (int j = 0; j < UNIT; ++j)
+            if (gc0 + j >= p.N) v[j] = 0.f;
+        }
+        if (STATS) {
+#pragma unroll
+          for (int j = 0; j < UNIT; ++j) { rsum += v[j]; rsq = __fmaf_rn(v[j], v[j], rsq); }
+        }
+        if (lane == 0) tma_store_wait_read<0>();        // previous box of this warp has left smem
+        __syncwarp();
+        if (OUTF32) {
+          float4* dst = reinterpret_cast<float4*>(stg + lane * (UNIT * 4));
+#pragma unroll
+          for (int j = 0; j < UNIT; j += 4) dst[j >> 2] = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          __half2 hh[UNIT / 2], ll[UNIT / 2];
+#pragma unroll
+          for (int j = 0; j < UNIT; j += 2) {
+            const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
+            const float2 hf = __half22float2(h2);
+            hh[j >> 1] = h2;
+            ll[j >> 1] = __floats2half2_rn(__fmul_rn(__fsub_rn(v[j], hf.x), F16_LO_SCALE),
+                                           __fmul_rn(__fsub_rn(v[j + 1], hf.y), F16_LO_SCALE));
+          }
+          uint4* dh = reinterpret_cast<uint4*>(stg + lane * (UNIT * 2));
+          uint4* dl = reinterpret_cast<uint4*>(stg + 32 * UNIT * 2 + lane * (UNIT * 2));
+          dh[0] = *reinterpret_cast<uint4*>(&hh[0]); dh[1] = *reinterpret_cast<uint4*>(&hh[4]);
+          dl[0] = *reinterpret_cast<uint4*>(&ll[0]); dl[1] = *reinterpret_cast<uint4*>(&ll[4]);
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (OUTF32) {
+            tma_store_2d(&tmO_f32, stg, gc0, wrow0);
+          } else {
+            tma_store_2d(&tmO_hi, stg, gc0, wrow0);
+            tma_store_2d(&tmO_lo, stg + 32 * UNIT * 2, gc0, wrow0);
+          }
+          tma_store_commit();
+        }
+      }
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+      if (STATS) {
+        // partial row sums of this column tile: combine the two 64-column halves of each row
+        float* sc = stats + (tc & 1) * (4 * 32 * 2 * 2);
+        float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
+        e[0] = rsum; e[1] = rsq;
+        named_bar_sync(1, 32 * EPI_WARPS);
+        if (half == 0 && row_ok) {
+          const float* f = sc + (q * 32 + lane) * 4;
+          p.out_sum[(size_t)ct * p.stat_stride + grow] = f[0] + f[2];
+          p.out_sq[(size_t)ct * p.stat_stride + grow] = f[1] + f[3];
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
 }
 
 // fp32 [n] -> fp16 pair
@@ -360,24 +700,28 @@ int launch_split(const float* src, Pair dst, size_t n, cudaStream_t stream) {
   return SSLAM_OK;
 }
 
-struct RowStats { float* mean; float* rstd; };
+struct RowStats { float* sum; float* sq; int parts; };   // [parts][stat_stride] partial row sums
+
+size_t stat_stride_of(int rows) { return align_up((size_t)rows, 64); }
+int stat_parts_of(int N) { return (N + BN - 1) / BN; }
 
 int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowStats a_ln, const float* s1,
-                Pair residual, int relu, float* out_f32, Pair out, RowStats out_stats, cudaStream_t stream) {
+                Pair residual, int relu, float* out_f32, Pair out, RowStats* out_stats, cudaStream_t stream) {
+  const bool pair = (K + BK - 1) / BK <= P_MAX_KB;                 // weight-stationary CTA-pair kernel
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_tensor_map_2d(&ta_hi, a.hi, rows, K, BM, BK, 2))) return rc;
   if ((rc = make_tensor_map_2d(&ta_lo, a.lo, rows, K, BM, BK, 2))) return rc;
-  if ((rc = make_tensor_map_2d(&tb_hi, w.hi, N, K, BN, BK, 2))) return rc;
-  if ((rc = make_tensor_map_2d(&tb_lo, w.lo, N, K, BN, BK, 2))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_hi, w.hi, N, K, pair ? 64 : BN, BK, 2))) return rc;
+  if ((rc = make_tensor_map_2d(&tb_lo, w.lo, N, K, pair ? 64 : BN, BK, 2))) return rc;
   // outputs: dense [32 rows][16 cols] boxes, no swizzle; unused maps alias a valid one
   CUtensorMap to_hi, to_lo, to_f32;
   if (out.hi) {
-    if ((rc = make_tensor_map_2d(&to_hi, out.hi, rows, N, 32, UNIT, 2, false))) return rc;
-    if ((rc = make_tensor_map_2d(&to_lo, out.lo, rows, N, 32, UNIT, 2, false))) return rc;
+    if ((rc = make_tensor_map_2d(&to_hi, out.hi, rows, N, 32, UNIT, 2, 0))) return rc;
+    if ((rc = make_tensor_map_2d(&to_lo, out.lo, rows, N, 32, UNIT, 2, 0))) return rc;
     to_f32 = to_hi;
   } else {
-    if ((rc = make_tensor_map_2d(&to_f32, out_f32, rows, N, 32, UNIT, 4, false))) return rc;
+    if ((rc = make_tensor_map_2d(&to_f32, out_f32, rows, N, 32, UNIT, 4, 0))) return rc;
     to_hi = to_f32; to_lo = to_f32;
   }
   static std::atomic<bool> configured{false};
@@ -389,8 +733,44 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.res_hi = residual.hi; gp.res_lo = residual.lo;
   gp.relu = relu; gp.out_f32 = out_f32; gp.out_hi = out.hi; gp.out_lo = out.lo;
-  gp.a_mean = a_ln.mean; gp.a_rstd = a_ln.rstd; gp.s1 = s1;
-  gp.out_mean = out_stats.mean; gp.out_rstd = out_stats.rstd;
+  gp.a_sum = a_ln.sum; gp.a_sq = a_ln.sq; gp.a_parts = a_ln.parts; gp.s1 = s1;
+  gp.out_sum = out_stats ? out_stats->sum : nullptr;
+  gp.out_sq = out_stats ? out_stats->sq : nullptr;
+  gp.stat_stride = stat_stride_of(rows);
+  gp.dbg = g_gemm_dbg;
+  if (pair) {
+    const int ntile = (N + BN - 1) / BN;
+    const int nsp = (rows + 2 * BM - 1) / (2 * BM);
+    int groups = (num_sms() / 2) / ntile;
+    if (groups > nsp) groups = nsp;
+    SSLAM_REQUIRE(groups >= 1, SSLAM_EUNSUPPORTED, "refiner: N=%d needs more column tiles than CTA pairs", N);
+    if (out_stats) out_stats->parts = ntile;
+    const unsigned grid = 2u * groups * ntile;
+    const bool ln = a_ln.sum != nullptr, res = residual.hi != nullptr, st = out_stats != nullptr;
+#define SSLAM_PAIR_LAUNCH(LN_, RES_, RELU_, F32_, ST_)                                                     \
+  do {                                                                                                     \
+    auto kfn = gemm_pair_kernel<LN_, RES_, RELU_, F32_, ST_>;                                              \
+    static std::atomic<bool> cfg{false};                                                                   \
+    if (!cfg.load()) {                                                                                     \
+      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL)); \
+      cfg.store(true);                                                                                     \
+    }                                                                                                      \
+    SSLAM_LAUNCH(KK_GEMM, stream,                                                                          \
+                 kfn<<<grid, NUM_THREADS, P_SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
+                                                                  to_f32, gp, groups));                    \
+  } while (0)
+    // the layer shapes of DescriptorRefiner: input projection, fc1, fc2 (+identity), output projection
+    if (!ln && !res && relu && !out_f32 && st) SSLAM_PAIR_LAUNCH(false, false, true, false, true);
+    else if (!ln && !res && relu && !out_f32 && !st) SSLAM_PAIR_LAUNCH(false, false, true, false, false);
+    else if (ln && !res && relu && !out_f32 && st) SSLAM_PAIR_LAUNCH(true, false, true, false, true);
+    else if (ln && res && relu && !out_f32 && st) SSLAM_PAIR_LAUNCH(true, true, true, false, true);
+    else if (ln && res && relu && !out_f32 && !st) SSLAM_PAIR_LAUNCH(true, true, true, false, false);
+    else if (!ln && !res && !relu && out_f32 && !st) SSLAM_PAIR_LAUNCH(false, false, false, true, false);
+    else SSLAM_REQUIRE(false, SSLAM_EUNSUPPORTED, "refiner: layer option combination not instantiated");
+#undef SSLAM_PAIR_LAUNCH
+    return SSLAM_OK;
+  }
+  if (out_stats) out_stats->parts = 1;
   const int strips = (rows + BM - 1) / BM;
   const int grid = strips < num_sms() ? strips : num_sms();        // persistent: one CTA per SM
   SSLAM_LAUNCH(KK_GEMM, stream,
@@ -459,8 +839,8 @@ extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, 
   (void)blocks;
   if (rows <= 0) return 0;
   const size_t r = (size_t)rows;
-  // pairs (4 B/element): x [r,C]; h_a, h_b, u [r,Hd];  fp32 raw [r,D];  6 row-stat vectors
-  return (r * C + 3 * r * Hd + r * D) * 4 + 6 * align_up(r * 4, 256) + 16 * 256;
+  // pairs (4 B/element): x [r,C]; h_a, h_b, u [r,Hd];  fp32 raw [r,D];  3 sets of partial row sums
+  return (r * C + 3 * r * Hd + r * D) * 4 + 6 * (size_t)stat_parts_of(Hd) * stat_stride_of(rows) * 4 + 16 * 256;
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
@@ -488,8 +868,9 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
     return q;
   };
   auto take_stats = [&]() {
-    RowStats st{reinterpret_cast<float*>(wp), reinterpret_cast<float*>(wp + align_up(r * 4, 256))};
-    wp += 2 * align_up(r * 4, 256);
+    const size_t n = (size_t)stat_parts_of(Hd) * stat_stride_of(rows);
+    RowStats st{reinterpret_cast<float*>(wp), reinterpret_cast<float*>(wp) + n, 0};
+    wp += 2 * n * 4;
     return st;
   };
   Pair xs = take_pair(r * C), h_a = take_pair(r * Hd), h_b = take_pair(r * Hd), u = take_pair(r * Hd);
@@ -503,7 +884,7 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
     return q;
   };
   const Pair none{nullptr, nullptr};
-  const RowStats no_stats{nullptr, nullptr};
+  const RowStats no_stats{nullptr, nullptr, 0};
 
   if (x) {
     if ((rc = launch_split(x, xs, r * C, stream))) return rc;
@@ -513,7 +894,7 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   }
   Pair w = next_w((size_t)Hd * C);                                        // descriptor_refiner.py:76
   if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], no_stats, nullptr, none, 1, nullptr, h_a,
-                        blocks ? st_a : no_stats, stream)))
+                        blocks ? &st_a : nullptr, stream)))
     return rc;
   Pair h_cur = h_a, h_nxt = h_b;
   RowStats st_cur = st_a, st_nxt = st_b;
@@ -523,14 +904,14 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
     const float* s1 = reinterpret_cast<const float*>(pk);
     const float* c0 = reinterpret_cast<const float*>(pk + align_up((size_t)Hd * 4, 256));
     pk += vec_bytes(Hd);
-    if ((rc = launch_gemm(h_cur, w, rows, Hd, Hd, c0, st_cur, s1, none, 1, nullptr, u, st_u, stream))) return rc;
+    if ((rc = launch_gemm(h_cur, w, rows, Hd, Hd, c0, st_cur, s1, none, 1, nullptr, u, &st_u, stream))) return rc;
     // fc2( LN2(u) ) + identity, ReLU
     w = next_w((size_t)Hd * Hd);
     s1 = reinterpret_cast<const float*>(pk);
     c0 = reinterpret_cast<const float*>(pk + align_up((size_t)Hd * 4, 256));
     pk += vec_bytes(Hd);
     const bool last = (b == blocks - 1);
-    if ((rc = launch_gemm(u, w, rows, Hd, Hd, c0, st_u, s1, h_cur, 1, nullptr, h_nxt, last ? no_stats : st_nxt,
+    if ((rc = launch_gemm(u, w, rows, Hd, Hd, c0, st_u, s1, h_cur, 1, nullptr, h_nxt, last ? nullptr : &st_nxt,
                           stream)))
       return rc;
     Pair tp = h_cur; h_cur = h_nxt; h_nxt = tp;
@@ -538,7 +919,12 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   }
   w = next_w((size_t)D * Hd);                                             // :83
   if ((rc = launch_gemm(h_cur, w, rows, D, Hd, params[3 + 8 * blocks], no_stats, nullptr, none, 0, raw, none,
-                        no_stats, stream)))
+                        nullptr, stream)))
     return rc;
   return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
 }
+
+// Debug aid for tools/: per-CTA cycle counters of gemm_pair_kernel ({MMA thread: total, wait_full,
+// wait_tempty, wait_weights; epilogue warp 2: total, wait_tfull, wait_store, tiles}, 8 int64 per CTA)
+// are written to buf (device) while buf != NULL.
+extern "C" void sslam_debug_gemm_stalls(long long* buf) { sslam::g_gemm_dbg = buf; }

@@ -16,8 +16,9 @@ namespace tc {
 // ------------------------------------------------------------------------------------ host side
 // Row-major 2-D tensor map [rows, cols] with a {box_cols, box_rows} box and 128-byte swizzle.
 // elem_bytes 4 (fp32/tf32) or 2 (bf16).  Returns SSLAM_OK or an error code.
+// swizzle_bytes: 128 (default), 64 or 0 (dense box).
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
-                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, bool swizzle128 = true);
+                       uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes = 128);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------ device side
@@ -179,6 +180,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// Same for the SWIZZLE_64B layout: rows of 64 bytes, groups of 8 rows (512 bytes) back to back
+// (a TMA box {64 bytes, R rows} with CU_TENSOR_MAP_SWIZZLE_64B); layout type 4.
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;
+  return d;
+}
 // Instruction descriptor (32 bit) for kind::f16 / kind::tf32, dense, fp32 accumulate, both
 // operands K-major:  [4,6) D format 1=f32   [7,10) A format   [10,13) B format
 //   (0 f16, 1 bf16, 2 tf32)   [15] A major 0=K   [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
@@ -208,6 +220,67 @@ __device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_
         "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
   }
+}
+
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster, on the two SMs of a TPC, execute one MMA with
+// M = 256 (each CTA owns 128 rows of A and of the accumulator) and share B (each holds N/2 rows).
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `smem_addr` (a shared::cta address of this CTA) in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release at CTA scope): a cluster-scope release would drain every outstanding
+  // memory operation of the thread (ERRBAR) — the data this barrier protects lives in TMEM and is
+  // ordered by tcgen05.fence::before_thread_sync
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose byte count is signalled on a barrier that may live in
+// the peer CTA (`bar_cluster_addr` is a shared::cluster address, e.g. from mapa_u32)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                 int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {   // one warp in EACH CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// D[tmem, both CTAs] (+)= A * B^T with M = 256; issued by one thread of the leader CTA (rank 0).  The
+// descriptors name the same shared-memory offsets in both CTAs.
+__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
