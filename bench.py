@@ -64,8 +64,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=600)
     ap.add_argument("--kpts", type=int, default=2048)
     ap.add_argument("--mode", default="auto", choices=["auto", "f32", "tf32x3", "f16x3", "bf16"])
-    ap.add_argument("--chunk", type=int, default=64)
-    ap.add_argument("--cpu-sample-frames", type=int, default=33)
+    ap.add_argument("--chunk", type=int, default=300, help="frames per extraction launch group (device-resident arm)")
+    ap.add_argument("--e2e-chunk", type=int, default=50, help="frames per host->device staging buffer (e2e arm)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=301)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -319,14 +320,14 @@ def run_b200(a):
         feat_h = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True).copy_(feat)
         out_h = None
         for _ in range(max(1, min(2, a.warmup))):
-            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.chunk, out_host=out_h,
+            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.e2e_chunk, out_host=out_h,
                                          ratio_thresh=0.8)
         fence()
         w0 = time.perf_counter()
         e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_beg.record()
         for _ in range(a.steps):
-            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.chunk, out_host=out_h,
+            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.e2e_chunk, out_host=out_h,
                                          ratio_thresh=0.8)
         e_end.record()
         fence()
@@ -412,7 +413,7 @@ def run_b200(a):
             "vs_baseline": None, "dtype": {"f32": "f32", "tf32x3": "tf32x3 (fp32 in/out)", "f16x3": "f16x3 (fp32 in/out)", "bf16": "bf16"}[mode_name],
             "data": "synthetic",
             "config": {"workload": workload_name(a), "frames_per_rank": T, "pairs_per_step": pairs_per_step,
-                       "similarity_mode": mode_name, "chunk": a.chunk,
+                       "similarity_mode": mode_name, "chunk": a.chunk, "e2e_chunk": a.e2e_chunk,
                        "launch": "CUDA graph replay (one graph per step)" if replay is not None else "eager",
                        "l2_policy": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)",
                        "parallelism": f"{world} independent sequence shard(s), final NCCL gather of match lists"

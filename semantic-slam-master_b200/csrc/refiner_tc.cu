@@ -79,6 +79,14 @@ struct GemmParams {
   long long* dbg;           // optional per-CTA stall counters (debug aid), or null
 };
 
+// 32 contiguous, 32-byte aligned bytes through the read-only path as one 256-bit load
+__device__ __forceinline__ void ldg_256(const void* ptr, uint4 (&d)[2]) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(d[0].x), "=r"(d[0].y), "=r"(d[0].z), "=r"(d[0].w), "=r"(d[1].x), "=r"(d[1].y), "=r"(d[1].z),
+                 "=r"(d[1].w)
+               : "l"(ptr));
+}
+
 // mean / rstd of row `grow` of the A operand from the producer's partial sums (fixed summation order)
 __device__ __forceinline__ void row_layernorm_scalars(const GemmParams& p, int grow, float& mean, float& rstd) {
   float sm = 0.f, sq = 0.f;
@@ -356,7 +364,7 @@ constexpr int P_SMEM_BARS = (2 * P_STAGES + 5) * 8 + 16;
 constexpr int P_SMEM_TOTAL = P_SMEM_B + P_SMEM_A + SMEM_TRANSP + SMEM_STATS + P_SMEM_VECS + P_SMEM_BARS + 1024;
 
 template <bool LN, bool RES, bool RELU, bool OUTF32, bool STATS>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  const __grid_constant__ CUtensorMap tmO_hi, const __grid_constant__ CUtensorMap tmO_lo,
@@ -378,16 +386,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int ntile = (p.N + BN - 1) / BN;
-  const int pair_id = blockIdx.x >> 1;
-  const int ct = pair_id % ntile, g = pair_id / ntile;
+  // cluster = the ntile CTA pairs that own the column tiles of the same strips; cluster rank = 2*ct + rank
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;                       // rank inside the CTA pair; 0 = MMA leader
+  const uint32_t leader = crank & ~1u;                    // cluster rank of this pair's leader
+  const int ntile = (p.N + BN - 1) / BN;                  // = multicast width
+  const int ct = (int)(crank >> 1), g = blockIdx.x / (2 * ntile);
   const int col_base = ct * BN;
   const int nsp = (p.rows + 2 * BM - 1) / (2 * BM);      // 256-row strip pairs
   const int nkb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    // a stage is free again when the MMAs of ALL pairs of the cluster have read it (it is refilled
+    // by a multicast that writes every CTA of the same rank)
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ntile); }
     mbar_init(bfull, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
     fence_barrier_init();
@@ -408,22 +420,35 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmA_lo);
       prefetch_tensormap(&tmB_hi); prefetch_tensormap(&tmB_lo);
       // resident weights: this CTA's 64 of the pair's 128 rows
-      const uint32_t bfull_leader = mapa_u32(smem_u32(bfull), 0);
+      const uint32_t bfull_leader = mapa_u32(smem_u32(bfull), leader);
       if (rank == 0) mbar_arrive_expect_tx(bfull, 2u * (uint32_t)nkb * 2u * B_HALF);
       for (int kb = 0; kb < nkb; ++kb) {
         tma_load_2d_pair(bres + kb * 2 * B_HALF, &tmB_hi, bfull_leader, kb * BK, col_base + (int)rank * 64);
         tma_load_2d_pair(bres + kb * 2 * B_HALF + B_HALF, &tmB_lo, bfull_leader, kb * BK, col_base + (int)rank * 64);
       }
+      // activations: the ntile CTAs of the same rank need the same 128-row tile of every k-block;
+      // they take turns fetching it and multicast it to all of them (L2 -> SM traffic / ntile)
+      uint16_t mc_mask = 0;
+      for (int j = 0; j < ntile; ++j) mc_mask |= (uint16_t)(1u << (2 * j + (int)rank));
       int stage = 0; uint32_t phase = 0;
+      int turn = 0;                                               // running k-block count modulo ntile
       for (int sp = g; sp < nsp; sp += groups) {
         const int row0 = sp * 2 * BM + (int)rank * BM;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = a_stages + stage * P_STAGE_BYTES;
-          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * P_STAGE_BYTES);
-          tma_load_2d_pair(st, &tmA_hi, full_leader, kb * BK, row0);
-          tma_load_2d_pair(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0);
+          if (turn == ct) {
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), leader);
+            if (ntile == 1) {
+              tma_load_2d_pair(st, &tmA_hi, full_leader, kb * BK, row0);
+              tma_load_2d_pair(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0);
+            } else {
+              tma_load_2d_pair_mc(st, &tmA_hi, full_leader, kb * BK, row0, mc_mask);
+              tma_load_2d_pair_mc(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0, mc_mask);
+            }
+          }
+          if (++turn == ntile) turn = 0;
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -431,6 +456,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {                               // ---- MMA issuer (leader CTA only)
       const uint32_t idesc = make_instr_desc(FMT_F16, 2 * BM, BN);
+      const uint16_t pair_mask = (uint16_t)(3u << leader);        // both CTAs of this pair
+      const uint16_t all_mask = (uint16_t)((1u << (2 * ntile)) - 1u);
       int stage = 0; uint32_t phase = 0;
       const bool dbg_on = p.dbg != nullptr;
       long long w_full = 0, w_tempty = 0, tq = 0, t_begin = clock64();
@@ -465,8 +492,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
             umma_ss_pair(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_ss_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
           }
-          tcgen05_commit_pair(&empty[stage], 3);
-          if (kb == nkb - 1) tcgen05_commit_pair(&tfull[acc], 3);
+          tcgen05_commit_pair(&empty[stage], all_mask);            // every CTA of the cluster: this pair is done with the stage
+          if (kb == nkb - 1) tcgen05_commit_pair(&tfull[acc], pair_mask);
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -484,8 +511,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int half = ew >> 2;
     unsigned char* stg = staging + ew * STG_BYTES;
     if (lane == 0) { prefetch_tensormap(&tmO_hi); prefetch_tensormap(&tmO_lo); prefetch_tensormap(&tmO_f32); }
-    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
-    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), leader);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), leader);
     const bool full_cols = col_base + BN <= p.N;          // no ragged columns in this pair's tile
     int tc = 0;
     for (int sp = g; sp < nsp; sp += groups, ++tc) {
@@ -499,11 +526,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const __half* res_h = RES ? p.res_hi + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
       const __half* res_l = RES ? p.res_lo + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
       auto load_res = [&](int gc, uint4 (&h)[2], uint4 (&l)[2]) {
-        if (gc + UNIT <= p.N) {
-          h[0] = __ldg(reinterpret_cast<const uint4*>(res_h + gc));
-          h[1] = __ldg(reinterpret_cast<const uint4*>(res_h + gc + 8));
-          l[0] = __ldg(reinterpret_cast<const uint4*>(res_l + gc));
-          l[1] = __ldg(reinterpret_cast<const uint4*>(res_l + gc + 8));
+        if (gc + UNIT <= p.N) {                         // one 32-byte sector per array: 256-bit loads
+          ldg_256(res_h + gc, h);
+          ldg_256(res_l + gc, l);
         } else {
           h[0] = h[1] = l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
           if (gc < p.N) {
@@ -707,7 +732,8 @@ int stat_parts_of(int N) { return (N + BN - 1) / BN; }
 
 int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowStats a_ln, const float* s1,
                 Pair residual, int relu, float* out_f32, Pair out, RowStats* out_stats, cudaStream_t stream) {
-  const bool pair = (K + BK - 1) / BK <= P_MAX_KB;                 // weight-stationary CTA-pair kernel
+  // weight-stationary CTA-pair kernel: weights must fit (K <= 384) and the ntile pairs form one cluster
+  const bool pair = (K + BK - 1) / BK <= P_MAX_KB && (N + BN - 1) / BN <= 4;
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
   int rc;
   if ((rc = make_tensor_map_2d(&ta_hi, a.hi, rows, K, BM, BK, 2))) return rc;
@@ -741,23 +767,31 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   if (pair) {
     const int ntile = (N + BN - 1) / BN;
     const int nsp = (rows + 2 * BM - 1) / (2 * BM);
-    int groups = (num_sms() / 2) / ntile;
-    if (groups > nsp) groups = nsp;
-    SSLAM_REQUIRE(groups >= 1, SSLAM_EUNSUPPORTED, "refiner: N=%d needs more column tiles than CTA pairs", N);
+    int groups = 0;
     if (out_stats) out_stats->parts = ntile;
-    const unsigned grid = 2u * groups * ntile;
     const bool ln = a_ln.sum != nullptr, res = residual.hi != nullptr, st = out_stats != nullptr;
 #define SSLAM_PAIR_LAUNCH(LN_, RES_, RELU_, F32_, ST_)                                                     \
   do {                                                                                                     \
     auto kfn = gemm_pair_kernel<LN_, RES_, RELU_, F32_, ST_>;                                              \
-    static std::atomic<bool> cfg{false};                                                                   \
-    if (!cfg.load()) {                                                                                     \
+    static std::atomic<int> max_clusters[5] = {};                 /* per cluster shape, 0 = not queried */  \
+    cudaLaunchConfig_t cfg = {};                                                                           \
+    cudaLaunchAttribute attr[1];                                                                           \
+    attr[0].id = cudaLaunchAttributeClusterDimension;                                                      \
+    attr[0].val.clusterDim.x = 2 * ntile; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;      \
+    cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = P_SMEM_TOTAL; cfg.stream = stream;            \
+    cfg.attrs = attr; cfg.numAttrs = 1;                                                                    \
+    int mcl = max_clusters[ntile].load();                                                                  \
+    if (mcl == 0) {                                                                                        \
       SSLAM_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL)); \
-      cfg.store(true);                                                                                     \
+      cfg.gridDim = dim3(2 * ntile);                                                                       \
+      SSLAM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&mcl, kfn, &cfg));                                   \
+      SSLAM_REQUIRE(mcl >= 1, SSLAM_EUNSUPPORTED, "refiner: no cluster of %d CTAs fits on this device", 2 * ntile); \
+      max_clusters[ntile].store(mcl);                                                                      \
     }                                                                                                      \
+    groups = mcl < nsp ? mcl : nsp;                               /* all clusters co-resident */            \
+    cfg.gridDim = dim3(2u * ntile * groups);                                                               \
     SSLAM_LAUNCH(KK_GEMM, stream,                                                                          \
-                 kfn<<<grid, NUM_THREADS, P_SMEM_TOTAL, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, \
-                                                                  to_f32, gp, groups));                    \
+                 cudaLaunchKernelEx(&cfg, kfn, ta_hi, ta_lo, tb_hi, tb_lo, to_hi, to_lo, to_f32, gp, groups)); \
   } while (0)
     // the layer shapes of DescriptorRefiner: input projection, fc1, fc2 (+identity), output projection
     if (!ln && !res && relu && !out_f32 && st) SSLAM_PAIR_LAUNCH(false, false, true, false, true);

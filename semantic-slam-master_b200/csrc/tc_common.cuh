@@ -56,11 +56,12 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded spin: a protocol bug traps (launch failure reported to the host) instead of hanging
-// the GPU.
+// Bounded wait: a protocol bug traps after ~2 s (launch failure reported to the host) instead of
+// hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
+  unsigned long long t0 = 0;
   for (uint32_t spin = 0; !ok; ++spin) {
     // the suspend-time hint lets the hardware park the thread instead of spinning on issue slots
     asm volatile(
@@ -70,9 +71,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(addr), "r"(parity), "r"(0x989680u)
+        : "r"(addr), "r"(parity), "r"(100000u)
         : "memory");
-    if (!ok && spin > (1u << 22)) __trap();
+    if (!ok && (spin & 63u) == 63u) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) __trap();
+    }
   }
 }
 
@@ -251,6 +257,18 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorM
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Same, multicast: the box lands at the same shared-memory offset in every CTA of `cta_mask` and the
+// bytes are signalled on the barrier at `bar_cluster_addr`'s offset in the pair leader (even rank) of
+// each destination CTA (bar_cluster_addr must name an even-ranked CTA).
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                    int c0, int c1, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "h"(cta_mask)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {   // one warp in EACH CTA

@@ -93,7 +93,7 @@ class FrontEnd:
                               scores1=sc, scores2=sc, **kw)[:3]
 
     @torch.no_grad()
-    def run_sequence(self, saliency, features, variant=matchers.M1, chunk=64, timers=None, **kw):
+    def run_sequence(self, saliency, features, variant=matchers.M1, chunk=256, timers=None, **kw):
         """Extract every frame once (in chunks) and match consecutive pairs.  Returns padded pair
         lists for the T-1 pairs, all on device."""
         T = saliency.shape[0]
@@ -122,7 +122,7 @@ class FrontEnd:
         return {k: v[s:e] for k, v in bank.items() if k != "keypoints_pixel"}
 
     @torch.no_grad()
-    def capture_sequence(self, saliency, features, variant=matchers.M1, chunk=64, **kw):
+    def capture_sequence(self, saliency, features, variant=matchers.M1, chunk=256, **kw):
         """Capture run_sequence on the given (static) input tensors into a CUDA graph.
 
         Every launch of the step (≈ 600 kernels of this library plus a few torch copies) is recorded
@@ -149,7 +149,8 @@ class FrontEnd:
         """End-to-end entry point for HOST data: pinned (T,H,W,1) saliency and (T,h,w,C) features
         are streamed to the device chunk by chunk on a copy stream (double-buffered, overlapping the
         kernels of the previous chunk), every frame is extracted once, consecutive pairs are matched,
-        and the match lists are copied back.  Returns host tensors (pairs, pair_scores, counts)."""
+        pairs are matched as soon as both of their frames are resident, and the match lists are
+        copied back as they are produced.  Returns host tensors (pairs, pair_scores, counts)."""
         dev = torch.device("cuda", torch.cuda.current_device())
         T = saliency_host.shape[0]
         compute = torch.cuda.current_stream()
@@ -165,6 +166,10 @@ class FrontEnd:
                                free=[torch.cuda.Event(), torch.cuda.Event()])
         st = self._stage
         feats = self._alloc_bank(T, dev)
+        if out_host is None:
+            out_host = (torch.empty((T - 1, self.K, 2), dtype=torch.int32, pin_memory=True),
+                        torch.empty((T - 1, self.K), dtype=torch.float32, pin_memory=True),
+                        torch.empty((T - 1,), dtype=torch.int32, pin_memory=True))
         copy.wait_stream(compute)
         for ci, s in enumerate(range(0, T, chunk)):
             e = min(T, s + chunk)
@@ -179,12 +184,15 @@ class FrontEnd:
             compute.wait_event(ready)
             self.extract(st["sal"][b][:e - s], st["feat"][b][:e - s], out=self._bank_slice(feats, s, e))
             st["free"][b].record(compute)
-        pairs, pscores, counts = self.match_consecutive(feats, variant, **kw)
-        if out_host is None:
-            out_host = (torch.empty(pairs.shape, dtype=pairs.dtype, pin_memory=True),
-                        torch.empty(pscores.shape, dtype=pscores.dtype, pin_memory=True),
-                        torch.empty(counts.shape, dtype=counts.dtype, pin_memory=True))
-        for dst, src in zip(out_host, (pairs, pscores, counts)):
-            dst.copy_(src, non_blocking=True)
+            # match every pair whose second frame has just been extracted, while later chunks are
+            # still crossing PCIe; the lists go back to the host as they are produced
+            p0 = max(s - 1, 0)
+            if e - 1 > p0:
+                bank = self.bank(feats)[p0:e]
+                sc = feats["scores"][p0:e]
+                res = matchers.match(bank, bank[1:], variant, num_pairs=e - 1 - p0, mode=self.sim_mode,
+                                     scores1=sc, scores2=sc[1:], **kw)[:3]
+                for dst, src in zip(out_host, res):
+                    dst[p0:e - 1].copy_(src, non_blocking=True)
         compute.synchronize()
         return out_host

@@ -366,6 +366,28 @@ def test_cuda_graph_replay_matches_eager(dev):
         assert torch.equal(pscores, e_pscores)
 
 
+def test_host_streaming_pipeline_matches_device_pipeline(dev):
+    """FrontEnd.run_sequence_host (pinned host buffers streamed chunk by chunk, pairs matched as
+    their frames arrive, lists copied back) returns exactly what the device-resident pass returns,
+    for chunk sizes that do and do not divide the sequence."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import matchers, synth
+    from sslam_b200.pipeline import FrontEnd
+    torch.manual_seed(0)
+    refiner = DescriptorRefiner(384, 384, 128, 4).to(dev)
+    fe = FrontEnd(refiner, num_keypoints=256, grid="pixel")
+    T = 7
+    sal, feat = synth.make_sequence(T, seq_id=5, height=96, width=128)
+    _, pairs, pscores, counts = fe.run_sequence(sal.to(dev), feat.to(dev), matchers.M1, chunk=T, ratio_thresh=0.8)
+    sal_h, feat_h = sal.pin_memory(), feat.pin_memory()
+    for chunk in (1, 3, 7, 16):
+        hp, hs, hc = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=chunk, ratio_thresh=0.8)
+        assert hp.shape == (T - 1, 256, 2) and hc.shape == (T - 1,)
+        assert torch.equal(hc, counts.cpu()), chunk
+        assert torch.equal(hp, pairs.cpu()), chunk
+        assert torch.equal(hs, pscores.cpu()), chunk
+
+
 def test_empty_and_degenerate_shapes(dev):
     """Empty batches / zero keypoints / tiny maps go through the C ABI without launching."""
     from sslam_b200 import ops
