@@ -447,6 +447,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
               tma_load_2d_pair_mc(st, &tmA_hi, full_leader, kb * BK, row0, mc_mask);
               tma_load_2d_pair_mc(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0, mc_mask);
             }
+            // the activations come from DRAM (a layer's input is far larger than L2): start the
+            // fetch of the same k-block of the NEXT strip pair now, one whole tile ahead
+            if (sp + groups < nsp) {
+              tma_prefetch_l2_2d(&tmA_hi, kb * BK, row0 + groups * 2 * BM);
+              tma_prefetch_l2_2d(&tmA_lo, kb * BK, row0 + groups * 2 * BM);
+            }
           }
           if (++turn == ntile) turn = 0;
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
@@ -570,6 +576,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       for (int un = 0; un < 64 / UNIT; ++un) {
         const int col0 = half * 64 + un * UNIT;         // first column of this unit inside the tile
         const int gc0 = col_base + col0;                // ... and in the output (warp-uniform)
+        // (one unit ahead only: a deeper prefetch makes ptxas spill, and registers that are the
+        // target of an in-flight tcgen05.ld must never be spilled or moved before tcgen05.wait::ld)
         uint4 rh[2], rl[2];
         if (RES) {
           rh[0] = nh[0]; rh[1] = nh[1]; rl[0] = nl[0]; rl[1] = nl[1];
