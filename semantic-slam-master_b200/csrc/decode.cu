@@ -220,6 +220,118 @@ __global__ void __launch_bounds__(256) decode_scan_strip_kernel(DecodeParams p, 
   for (u32 i = threadIdx.x; i < nstaged; i += blockDim.x) cand[sbase + i] = sbuf[i];
 }
 
+// K1, vector path (radius 1..3, W % 4 == 0, 16-byte aligned maps): as above, but every lane owns FOUR
+// consecutive columns loaded as one float4, so a warp row is one 512-byte request and the per-pixel
+// instruction count drops ~3x (the scalar kernel is issue bound at 14 % of HBM bandwidth).  Lanes
+// 0 and 31 are halo lanes (a whole float4 each side, which keeps the loads aligned); lanes 1..30
+// produce 120 output columns.  The horizontal maxima use the neighbours' edge values (2R
+// shuffles), the vertical ones a ring of the last 2R+1 row maxima with compile-time slots.
+template <int R>
+__global__ void __launch_bounds__(256) decode_scan_vec_kernel(DecodeParams p, int nstrips, int nseg,
+                                                              int seg_rows) {
+  constexpr int WIN = 2 * R + 1, OUTW = 120, CAP = 2048;
+  __shared__ u64 sbuf[CAP];
+  __shared__ u32 scount, sbase;
+  const int lane = threadIdx.x & 31;
+  const int per_img = nstrips * nseg;
+  const int ctas_per_img = (per_img + 7) / 8;                 // a CTA never straddles two images
+  const int b = blockIdx.x / ctas_per_img;
+  const int rem = (blockIdx.x - b * ctas_per_img) * 8 + (threadIdx.x >> 5);
+  const bool active = rem < per_img;
+  const int seg = rem / nstrips, strip = rem - seg * nstrips;
+  if (threadIdx.x == 0) scount = 0;
+  __syncthreads();
+  const int H = p.H, W = p.W;
+  const int x = strip * OUTW - 4 + 4 * lane;                  // first of this lane's four columns
+  const bool col_ok = (x >= 0) && (x < W);                    // W % 4 == 0: all four or none
+  const bool out_lane = (lane >= 1) && (lane <= 30) && col_ok;
+  const int y0 = seg * seg_rows, y1 = active ? min(H, y0 + seg_rows) : y0 - R;
+  const int y_end = y1 + R;                                   // rows [y0-R, y_end) are loaded
+  const size_t img = (size_t)b * H * W;
+  const float NEG_INF = __int_as_float(0xff800000);
+  const float min_keep = fminf(p.floor, LOWER_FLOOR);
+  ImgHeader* hdr = p.hdr + b;
+  u64* cand = p.cand + (size_t)b * H * W;
+
+  auto ldrow = [&](int y) -> float4 {
+    float4 v = make_float4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
+    if (col_ok && y >= 0 && y < H && y < y_end) {
+      v = __ldg(reinterpret_cast<const float4*>(p.sal + img + (size_t)y * W + x));
+      if (p.from_logits) { v.x = sigmoid_f32(v.x); v.y = sigmoid_f32(v.y); v.z = sigmoid_f32(v.z); v.w = sigmoid_f32(v.w); }
+    }
+    return v;
+  };
+  float4 pre[WIN];
+#pragma unroll
+  for (int i = 0; i < WIN; ++i) pre[i] = ldrow(y0 - R + i);
+  float hwin[WIN][4], cwin[WIN][4];                          // rings: row maxima / centre values
+#pragma unroll
+  for (int i = 0; i < WIN; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { hwin[i][c] = NEG_INF; cwin[i][c] = NEG_INF; }
+
+  for (int yy = y0 - R; yy < y_end; yy += WIN) {
+#pragma unroll
+    for (int u = 0; u < WIN; ++u) {
+      const int yc = yy + u;
+      const float4 v4 = pre[u];
+      pre[u] = ldrow(yc + WIN);
+      if (yc < y_end) {                                       // warp-uniform
+        // e[] = R values of the left neighbour, own four, R values of the right neighbour
+        float e[4 + 2 * R];
+        const float own[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) e[R + c] = own[c];
+#pragma unroll
+        for (int d = 0; d < R; ++d) {
+          e[d] = __shfl_up_sync(0xffffffffu, own[4 - R + d], 1);
+          e[R + 4 + d] = __shfl_down_sync(0xffffffffu, own[d], 1);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float hm = e[c];
+#pragma unroll
+          for (int d = 1; d < WIN; ++d) hm = fmaxf(hm, e[c + d]);
+          hwin[u][c] = hm;
+          cwin[u][c] = own[c];
+        }
+        const int yo = yc - R;                                // output row whose window is complete
+        if (yo >= y0) {                                       // warp-uniform
+          unsigned mask = 0;
+          float cv[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float m = hwin[0][c];
+#pragma unroll
+            for (int i = 1; i < WIN; ++i) m = fmaxf(m, hwin[i][c]);
+            cv[c] = cwin[(u + WIN - R) % WIN][c];
+            if (out_lane && (cv[c] == m) && (cv[c] > min_keep)) mask |= 1u << c;
+          }
+          if (mask) {
+            // local maxima are sparse (~4 % of the pixels): the few lanes that found one append it
+            // to the CTA's staging list themselves (order in the list is irrelevant, K2 sorts keys)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if ((mask >> c) & 1u) {
+                const u32 lin = (u32)(yo * W + x + c);
+                const u64 key = ((u64)__float_as_uint(cv[c]) << 32) | (u64)(0xffffffffu - lin);
+                const u32 pos = atomicAdd(&scount, 1u);
+                if (pos < (u32)CAP) sbuf[pos] = key;
+                else cand[atomicAdd(&hdr->cand_count, 1u)] = key;   // staging list full (plateau maps)
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const u32 nstaged = min(scount, (u32)CAP);
+  if (threadIdx.x == 0 && nstaged) sbase = atomicAdd(&hdr->cand_count, nstaged);
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < nstaged; i += blockDim.x) cand[sbase + i] = sbuf[i];
+}
+
 // Plain NMS output (drop-in for _apply_nms)
 __global__ void __launch_bounds__(SCAN_THREADS) nms_kernel(const float* sal, int H, int W, int r,
                                                            float* out) {
@@ -346,10 +458,19 @@ __global__ void __launch_bounds__(256) decode_count_kernel(DecodeParams p, int c
   const float kth = __uint_as_float((u32)(hdr->kth_key >> 32));
   const int n = p.H * p.W;
   const size_t img = (size_t)b * n;
-  const int per = (n + chunks_per_img - 1) / chunks_per_img;
+  int per = (n + chunks_per_img - 1) / chunks_per_img;
+  per = (per + 3) & ~3;                                       // chunk boundaries stay 16-byte aligned
   const int beg = chunk * per, end = min(n, beg + per);
   u32 c = 0;
-  for (int i = beg + threadIdx.x; i < end; i += 256) c += (load_px(p, img + i) < kth) ? 1u : 0u;
+  if ((n & 3) == 0 && (reinterpret_cast<uintptr_t>(p.sal) & 15) == 0) {
+    for (int i = beg + 4 * (int)threadIdx.x; i < end; i += 4 * 256) {        // n % 4 == 0: whole float4s
+      float4 v = __ldg(reinterpret_cast<const float4*>(p.sal + img + i));
+      if (p.from_logits) { v.x = sigmoid_f32(v.x); v.y = sigmoid_f32(v.y); v.z = sigmoid_f32(v.z); v.w = sigmoid_f32(v.w); }
+      c += (v.x < kth ? 1u : 0u) + (v.y < kth ? 1u : 0u) + (v.z < kth ? 1u : 0u) + (v.w < kth ? 1u : 0u);
+    }
+  } else {
+    for (int i = beg + threadIdx.x; i < end; i += 256) c += (load_px(p, img + i) < kth) ? 1u : 0u;
+  }
   c = block_reduce_sum(c, red);
   if (threadIdx.x == 0 && c) atomicAdd(&hdr->below_count, c);
 }
@@ -549,7 +670,18 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
   SSLAM_CHECK_CUDA(cudaMemsetAsync(p.hdr, 0, (size_t)B * sizeof(ImgHeader), stream));
 
   const int r = nms_radius;
-  if (r >= 1 && r <= 3) {
+  const bool vec_ok = (W % 4 == 0) && (W >= 64) && ((reinterpret_cast<uintptr_t>(sal) & 15) == 0);
+  if (r >= 1 && r <= 3 && vec_ok) {
+    const int nstrips = (W + 119) / 120;                       // 120 output columns per warp
+    int nseg = (H + 63) / 64;                                  // ~64 rows per warp
+    const int seg_rows = (H + nseg - 1) / nseg;
+    nseg = (H + seg_rows - 1) / seg_rows;
+    const unsigned blocks = (unsigned)(((nstrips * nseg + 7) / 8) * B);
+    SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
+                 if (r == 1) decode_scan_vec_kernel<1><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows);
+                 else if (r == 2) decode_scan_vec_kernel<2><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows);
+                 else decode_scan_vec_kernel<3><<<blocks, 256, 0, stream>>>(p, nstrips, nseg, seg_rows));
+  } else if (r >= 1 && r <= 3) {
     const int outw = 32 - 2 * r;
     const int nstrips = (W + outw - 1) / outw;
     int nseg = (H + 63) / 64;                                  // ~64 rows per warp

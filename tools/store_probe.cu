@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(256, 1) probe(const __grid_constant__ CUtensor
       unsigned char* g = gbuf + (size_t)(row_base + lane) * row_pitch + (i * 32) % 2048;
       *reinterpret_cast<uint4*>(g) = make_uint4(i, i, i, i);
       *reinterpret_cast<uint4*>(g + 16) = make_uint4(i, i, i, i);
+    } else if (mode == 5) {
+      unsigned char* g = gbuf + (size_t)(row_base + lane) * row_pitch + (i * 32) % 2048;
+      asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(g), "r"(i) : "memory");
     } else {
       // 4 instructions x (4 rows x 128 B) = 32 rows x 64 B ... use 8 instr for 32 rows x 128 B
 #pragma unroll
@@ -66,10 +69,10 @@ int main() {
   if (make_tensor_map_2d(&t32, gbuf, rows, 1024, 32, 16, 2, 0) || make_tensor_map_2d(&t64, gbuf, rows, 1024, 32, 32, 2, 0) ||
       make_tensor_map_2d(&t128, gbuf, rows, 1024, 32, 64, 2, 128)) { printf("tensor map failed\n"); return 1; }
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-  const char* names[] = {"TMA box 32x32B", "TMA box 32x64B", "TMA box 32x128B (sw128)", "st.global lane=row 32B", "st.global coalesced 32x128B"};
-  const int bytes[] = {1024, 2048, 4096, 1024, 4096};
+  const char* names[] = {"TMA box 32x32B", "TMA box 32x64B", "TMA box 32x128B (sw128)", "st.global lane=row 32B", "st.global coalesced 32x128B", "st.global.v8 lane=row 32B"};
+  const int bytes[] = {1024, 2048, 4096, 1024, 4096, 1024};
   for (int nw : {1, 8}) {
-    for (int mode = 0; mode < 5; ++mode) {
+    for (int mode = 0; mode < 6; ++mode) {
       for (int rep = 0; rep < 2; ++rep) probe<<<sms, 256, 80 * 1024>>>(t32, t64, t128, gbuf, pitch, mode, nw, dout);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error: %s\n", cudaGetErrorString(e)); return 1; }
