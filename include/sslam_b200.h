@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSLAM_ABI_VERSION 1
+#define SSLAM_ABI_VERSION 2
 
 enum {
   SSLAM_OK = 0,
@@ -128,9 +128,11 @@ int sslam_gather_bilinear_f32(const float* feat, const float* kpts, int B, int h
 
 /* Row-wise L2 normalisation, the tail of DescriptorRefiner.forward
  * (models/descriptor_refiner.py:86): out = in / max(||in||_2, eps).
- *   in [rows,D] fp32;  out_f32 [rows,D] fp32 or NULL;  out_bf16 [rows,D] bf16 or NULL. */
+ *   in [rows,D] fp32;  out_f32 [rows,D] fp32 or NULL;  out_bf16 [rows,D] bf16 or NULL;
+ *   out_hi / out_lo [rows,D] fp16 or both NULL: the normalised value as the fp16 pair
+ *   hi + lo*2^-11 that sslam_match_top2(SSLAM_SIM_F16X3) multiplies (saves its own split pass). */
 int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f32,
-                      void* out_bf16, void* stream);
+                      void* out_bf16, void* out_hi, void* out_lo, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DescriptorRefiner forward (models/descriptor_refiner.py:58-91, 108-126): Linear+ReLU, `blocks`
@@ -142,7 +144,8 @@ int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f3
  *   packed : device buffer of sslam_refiner_packed_bytes(), filled once per weight set by
  *            sslam_refiner_pack_weights() (tf32 hi/lo copies of the Linear weights)
  *   x [rows,C] fp32 (or NULL with the pair x_hi/x_lo [rows,C] fp16 from sslam_gather_bilinear_f32)
- *   -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16, unit L2 norm
+ *   -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16 and/or the fp16 pair out_hi/out_lo
+ *      [rows,D] (see sslam_l2norm_rows), unit L2 norm
  * Arithmetic: fp16 hi/lo pairs (22 significant bits), three kind::f16 MMAs per product, fp32
  * accumulation; |activation| must stay below 65504.  C, Hd multiples of 8, D of 4; Hd <= 1024;
  * LayerNorm eps is torch's default 1e-5.
@@ -154,8 +157,8 @@ size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, int blocks)
 int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
                               const void* x_hi, const void* x_lo,
                               int rows, int C, int Hd, int D, int blocks, float eps_norm,
-                              float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
-                              void* stream);
+                              float* out_f32, void* out_bf16, void* out_hi, void* out_lo,
+                              void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Matching primitive shared by M1..M5: over the virtual S_p = D1_p . D2_p^T (never stored)
@@ -166,12 +169,15 @@ int sslam_refiner_forward_f32(const float* const* params, const void* packed, co
  * bank2 = bank1 + N*D for consecutive-frame matching).  Pair p reads set a of bank1 and set b of
  * bank2 where (a,b) = pair_index[p] if pair_index != NULL (int32 [P,2], device) else (p,p).  `dtype` is SSLAM_SIM_*; banks are fp32 for
  * SSLAM_SIM_F32 / TF32X3 / F16X3 and bf16 for SSLAM_SIM_BF16.  D % 4 == 0 (8 for bf16/f16x3), D <= 256.
+ * SSLAM_SIM_F16X3 only: when bank1_lo and bank2_lo are non-NULL the banks are already split —
+ * bank1 / bank2 are the fp16 hi arrays and bank1_lo / bank2_lo the fp16 lo arrays written by
+ * sslam_l2norm_rows / sslam_refiner_forward_f32 — and no split pass runs.
  * Replaces visualize_matches.py:105-109,117-119; visualize_matches_sequence.py:144-146;
  * test/test_descriptor_quality.py:116-130; train.py:422-424; test/test_tracking.py:159-160.
  */
 size_t sslam_match_workspace_bytes(int F1, int F2, int P, int N, int M, int D, int dtype);
-int sslam_match_top2(const void* bank1, int F1, const void* bank2, int F2,
-                     const int32_t* pair_index, int dtype,
+int sslam_match_top2(const void* bank1, const void* bank1_lo, int F1, const void* bank2,
+                     const void* bank2_lo, int F2, const int32_t* pair_index, int dtype,
                      int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                      int32_t* nn21, float* best21, void* ws, size_t ws_bytes, void* stream);
 

@@ -288,7 +288,7 @@ gather_band_kernel(const float* __restrict__ feat, const float* __restrict__ kpt
 template <bool VEC4>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
 l2norm_kernel(const float* __restrict__ in, int rows, int D, float eps, float* __restrict__ out_f32,
-              __nv_bfloat16* __restrict__ out_bf16) {
+              __nv_bfloat16* __restrict__ out_bf16, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -316,12 +316,28 @@ l2norm_kernel(const float* __restrict__ in, int rows, int D, float eps, float* _
         uint2 pk = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
         *reinterpret_cast<uint2*>(out_bf16 + (size_t)row * D + c) = pk;
       }
+      if (out_hi) {                                         // fp16 pair for the f16x3 matcher
+        __half h4[4], l4[4];
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          h4[i] = __float2half_rn(rr[i]);
+          l4[i] = __float2half_rn(__fmul_rn(__fsub_rn(rr[i], __half2float(h4[i])), 2048.0f));
+        }
+        *reinterpret_cast<uint2*>(out_hi + (size_t)row * D + c) = *reinterpret_cast<uint2*>(h4);
+        *reinterpret_cast<uint2*>(out_lo + (size_t)row * D + c) = *reinterpret_cast<uint2*>(l4);
+      }
     }
   } else {
     for (int c = lane; c < D; c += 32) {
       float r = __fdiv_rn(__ldg(src + c), denom);
       if (out_f32) out_f32[(size_t)row * D + c] = r;
       if (out_bf16) out_bf16[(size_t)row * D + c] = __float2bfloat16_rn(r);
+      if (out_hi) {
+        const __half h = __float2half_rn(r);
+        out_hi[(size_t)row * D + c] = h;
+        out_lo[(size_t)row * D + c] = __float2half_rn(__fmul_rn(__fsub_rn(r, __half2float(h)), 2048.0f));
+      }
     }
   }
 }
@@ -389,23 +405,27 @@ extern "C" int sslam_gather_bilinear_f32(const float* feat, const float* kpts, i
 }
 
 extern "C" int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f32,
-                                 void* out_bf16, void* stream_) {
+                                 void* out_bf16, void* out_hi_, void* out_lo_, void* stream_) {
+  __half* out_hi = static_cast<__half*>(out_hi_);
+  __half* out_lo = static_cast<__half*>(out_lo_);
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   SSLAM_REQUIRE(rows >= 0 && D > 0, SSLAM_EINVAL, "l2norm: bad size");
   if (rows == 0) return SSLAM_OK;
-  SSLAM_REQUIRE(in && (out_f32 || out_bf16), SSLAM_EINVAL, "l2norm: null pointer");
+  SSLAM_REQUIRE(in && (out_f32 || out_bf16 || out_hi), SSLAM_EINVAL, "l2norm: null pointer");
+  SSLAM_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), SSLAM_EINVAL, "l2norm: pair outputs go together");
   const unsigned blocks = (unsigned)((rows + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
   const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0) &&
                    (!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0) &&
-                   (!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0);
+                   (!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out_hi) & 7) == 0) && ((reinterpret_cast<uintptr_t>(out_lo) & 7) == 0);
   SSLAM_LAUNCH(KK_L2NORM, stream,
                if (vec)
       l2norm_kernel<true><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
-          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_hi, out_lo);
     else
       l2norm_kernel<false><<<blocks, WARPS_PER_BLOCK * 32, 0, stream>>>(
-          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16)));
+          in, rows, D, eps, out_f32, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_hi, out_lo));
   return SSLAM_OK;
 }

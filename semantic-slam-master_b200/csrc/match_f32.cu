@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalizeParams f) {
 }  // namespace
 
 // implemented in match_tc.cu
-int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
+int match_top2_tc(const void* bank1, const void* bank1_lo, int F1, const void* bank2, const void* bank2_lo,
+                  int F2, const int32_t* pair_index,
                   int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                   u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream);
 size_t match_tc_extra_workspace(int P, int N, int M, int D, int dtype, int F1, int F2);
@@ -313,8 +314,8 @@ extern "C" size_t sslam_match_workspace_bytes(int F1, int F2, int P, int N, int 
   return base;
 }
 
-extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, int F2,
-                                const int32_t* pair_index,
+extern "C" int sslam_match_top2(const void* bank1, const void* bank1_lo, int F1, const void* bank2,
+                                const void* bank2_lo, int F2, const int32_t* pair_index,
                                 int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12,
                                 float* second12, int32_t* nn21, float* best21, void* ws,
                                 size_t ws_bytes, void* stream_) {
@@ -332,9 +333,14 @@ extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, in
                 SSLAM_EINVAL, "match: unknown dtype %d", dtype);
   SSLAM_REQUIRE(F1 > 0 && F2 > 0 && (pair_index || (F1 >= P && F2 >= P)), SSLAM_EINVAL,
                 "match: banks hold %d / %d sets but %d implicit pairs were requested", F1, F2, P);
-  SSLAM_REQUIRE(ws_bytes >= sslam_match_workspace_bytes(F1, F2, P, N, M, D, dtype), SSLAM_EWORKSPACE,
-                "match: workspace %zu < %zu", ws_bytes,
-                sslam_match_workspace_bytes(F1, F2, P, N, M, D, dtype));
+  const bool presplit = bank1_lo != nullptr || bank2_lo != nullptr;
+  SSLAM_REQUIRE(!presplit || (dtype == SSLAM_SIM_F16X3 && bank1_lo && bank2_lo), SSLAM_EINVAL,
+                "match: pre-split banks need SSLAM_SIM_F16X3 and both lo arrays");
+  {
+    const size_t need = presplit ? align_up((size_t)P * M * sizeof(u64), 256)
+                                 : sslam_match_workspace_bytes(F1, F2, P, N, M, D, dtype);
+    SSLAM_REQUIRE(ws_bytes >= need, SSLAM_EWORKSPACE, "match: workspace %zu < %zu", ws_bytes, need);
+  }
   SSLAM_REQUIRE((reinterpret_cast<uintptr_t>(bank1) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(bank2) & 15) == 0, SSLAM_EINVAL,
                 "match: descriptor banks must be 16-byte aligned");
@@ -359,7 +365,8 @@ extern "C" int sslam_match_top2(const void* bank1, int F1, const void* bank2, in
     SSLAM_LAUNCH(KK_MATCH_F32, stream,
                  match_f32_kernel<<<grid, THREADS, smem, stream>>>(mp));
   } else {
-    rc = match_top2_tc(bank1, F1, bank2, F2, pair_index, dtype, P, N, M, D, nn12, best12, second12, colkeys,
+    rc = match_top2_tc(bank1, bank1_lo, F1, bank2, bank2_lo, F2, pair_index, dtype, P, N, M, D, nn12, best12,
+                       second12, colkeys,
                        reinterpret_cast<char*>(ws) + colbytes, ws_bytes - colbytes, stream);
     if (rc) return rc;
   }

@@ -742,7 +742,8 @@ static int launch_res(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
   return SSLAM_OK;
 }
 
-int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const int32_t* pair_index,
+int match_top2_tc(const void* bank1, const void* bank1_lo, int F1, const void* bank2, const void* bank2_lo,
+                  int F2, const int32_t* pair_index,
                   int dtype, int P, int N, int M, int D, int32_t* nn12, float* best12, float* second12,
                   u64* colkeys, void* ws_extra, size_t ws_extra_bytes, cudaStream_t stream) {
   TcParams tp;
@@ -762,6 +763,15 @@ int match_top2_tc(const void* bank1, int F1, const void* bank2, int F2, const in
   const bool f16 = (dtype == SSLAM_SIM_F16X3);
   const size_t e = f16 ? 2 : 4;
   SSLAM_REQUIRE(!f16 || D % 8 == 0, SSLAM_EUNSUPPORTED, "match(f16x3): D=%d must be a multiple of 8", D);
+  if (f16 && bank1_lo && bank2_lo) {
+    // banks arrive as fp16 (hi, lo) pairs (written by the L2-normalisation kernel): nothing to split
+    const uint64_t rows2p = (uint64_t)F2 * M;
+    if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&a_lo, bank1_lo, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, bank2, rows2p, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&b_lo, bank2_lo, rows2p, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    return launch_res<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
+  }
   SSLAM_REQUIRE(ws_extra_bytes >= match_tc_extra_workspace(P, N, M, D, dtype, F1, F2), SSLAM_EWORKSPACE,
                 "match(split): workspace too small");
   const float* f1 = static_cast<const float*>(bank1);

@@ -891,14 +891,14 @@ extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
                                          const void* x_hi, const void* x_lo,
                                          int rows, int C, int Hd, int D, int blocks, float eps_norm,
-                                         float* out_f32, void* out_bf16, void* ws, size_t ws_bytes,
-                                         void* stream_) {
+                                         float* out_f32, void* out_bf16, void* out_hi, void* out_lo,
+                                         void* ws, size_t ws_bytes, void* stream_) {
   int rc = check_device();
   if (rc) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
   SSLAM_REQUIRE(rows >= 0, SSLAM_EINVAL, "refiner: negative rows");
   if (rows == 0) return SSLAM_OK;
-  SSLAM_REQUIRE(params && packed && (x || (x_hi && x_lo)) && ws && (out_f32 || out_bf16), SSLAM_EINVAL,
+  SSLAM_REQUIRE(params && packed && (x || (x_hi && x_lo)) && ws && (out_f32 || out_bf16 || out_hi), SSLAM_EINVAL,
                 "refiner: null pointer");
   SSLAM_REQUIRE(C % 8 == 0 && Hd % 8 == 0 && D % 4 == 0 && Hd <= MAX_N && D <= MAX_N, SSLAM_EUNSUPPORTED,
                 "refiner: C and hidden must be multiples of 8, D of 4, hidden and D <= 1024 (C=%d Hd=%d D=%d)", C, Hd, D);
@@ -966,7 +966,7 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   if ((rc = launch_gemm(h_cur, w, rows, D, Hd, params[3 + 8 * blocks], no_stats, nullptr, none, 0, raw, none,
                         nullptr, stream)))
     return rc;
-  return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, stream_);   // :86
+  return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, out_hi, out_lo, stream_);   // :86
 }
 
 // Debug aid for tools/: per-CTA cycle counters of gemm_pair_kernel ({MMA thread: total, wait_full,

@@ -74,10 +74,12 @@ class DescriptorRefiner(nn.Module):
             self._plan_key = key
         return self._plan_obj
 
-    def forward_fused(self, dino_features, want_bf16: bool = False, out=None, out16=None):
+    def forward_fused(self, dino_features, want_bf16: bool = False, out=None, out16=None, out_pair=None):
         """(..., C) fp32 — or the fp16 (hi, lo) pair of ops.gather_bilinear(pair=True) —
-        -> (rows, D) unit-norm fp32 [, bf16 copy] through sslam_refiner_forward_f32."""
-        return ops.refiner_forward(self._plan(), dino_features, want_bf16=want_bf16, out=out, out16=out16)
+        -> (rows, D) unit-norm fp32 [, bf16 copy] [, fp16 pair into out_pair] through
+        sslam_refiner_forward_f32."""
+        return ops.refiner_forward(self._plan(), dino_features, want_bf16=want_bf16, out=out, out16=out16,
+                                   out_pair=out_pair)
 
     def forward(self, dino_features: torch.Tensor) -> torch.Tensor:
         """(B, N, C) features at keypoints -> (B, N, output_dim) unit-norm descriptors."""

@@ -25,16 +25,18 @@ SIGNATURES = {
     "sslam_nms_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "sslam_gather_bilinear_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                           c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "sslam_l2norm_rows": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "sslam_l2norm_rows": (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
     "sslam_refiner_packed_bytes": (c_size_t, [c_int] * 4),
     "sslam_refiner_pack_weights": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int, c_void_p,
                                            c_size_t, c_void_p]),
     "sslam_refiner_workspace_bytes": (c_size_t, [c_int] * 5),
     "sslam_refiner_forward_f32": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
-                                          c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
-                                          c_size_t, c_void_p]),
+                                          c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p, c_size_t, c_void_p]),
     "sslam_match_workspace_bytes": (c_size_t, [c_int] * 7),
-    "sslam_match_top2": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int,
+    "sslam_match_top2": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                 c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
     "sslam_match_finalize": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int,
@@ -67,7 +69,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.sslam_abi_version() != 1:
+        if lib.sslam_abi_version() != 2:
             raise ImportError("libsslam_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

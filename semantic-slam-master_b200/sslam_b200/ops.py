@@ -128,8 +128,10 @@ def gather_bilinear(features, keypoints, pixel_coords=False, out=None, pair=Fals
     return (hi, lo) if pair else out
 
 
-def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False):
-    """x (..., D) fp32 -> x / max(||x||, eps); optionally also a bf16 copy."""
+def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False, pair=None):
+    """x (..., D) fp32 -> x / max(||x||, eps); optionally also a bf16 copy.  `pair` = (hi, lo) fp16
+    tensors of x's shape additionally receive the result as the fp16 pair hi + lo*2^-11 that
+    match_top2(mode=SIM_F16X3) consumes directly."""
     lib = _lib.load()
     _need_cuda(x)
     xc = x.contiguous()
@@ -139,9 +141,20 @@ def l2norm_rows(x, eps=1e-12, out=None, out_bf16=None, want_bf16=False):
         out = torch.empty_like(xc)
     if want_bf16 and out_bf16 is None:
         out_bf16 = torch.empty(xc.shape, dtype=torch.bfloat16, device=xc.device)
-    _lib.check(lib.sslam_l2norm_rows(_ptr(xc), rows, D, float(eps), _ptr(out), _ptr(out_bf16),
-                                     _stream()))
+    hi, lo = _check_pair(pair, rows * D)
+    _lib.check(lib.sslam_l2norm_rows(_ptr(xc), rows, D, float(eps), _ptr(out), _ptr(out_bf16), _ptr(hi),
+                                     _ptr(lo), _stream()))
     return (out, out_bf16) if want_bf16 else out
+
+
+def _check_pair(pair, numel):
+    if pair is None:
+        return None, None
+    hi, lo = pair
+    for t in (hi, lo):
+        if t.dtype != torch.float16 or not t.is_contiguous() or t.numel() != numel:
+            raise RuntimeError("fp16 pair outputs must be contiguous fp16 tensors of the result's size")
+    return hi, lo
 
 
 class RefinerPlan:
@@ -165,9 +178,10 @@ class RefinerPlan:
                                                   _ptr(self.packed), nbytes, _stream()))
 
 
-def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=None, out16=None):
+def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=None, out16=None, out_pair=None):
     """x (..., C) fp32 — or the (hi, lo) fp16 pair from gather_bilinear(pair=True) —
-    -> unit-norm descriptors (rows, D) fp32 [and bf16 copy]."""
+    -> unit-norm descriptors (rows, D) fp32 [and bf16 copy] [and, into out_pair = (hi, lo), the fp16
+    pair the f16x3 matcher multiplies]."""
     lib = _lib.load()
     x_hi = x_lo = None
     if isinstance(x, (tuple, list)):
@@ -192,12 +206,14 @@ def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=Non
     for t in (out, out16):
         if t is not None and (not t.is_contiguous() or t.numel() != rows * plan.D):
             raise RuntimeError("refiner_forward: output buffers must be contiguous (rows, D)")
+    p_hi, p_lo = _check_pair(out_pair, rows * plan.D)
     need = lib.sslam_refiner_workspace_bytes(rows, plan.C, plan.Hd, plan.D, plan.blocks)
     ws = workspace if workspace is not None else _ws("refiner", need, xc_dev)
     _lib.check(lib.sslam_refiner_forward_f32(plan.ptrs, _ptr(plan.packed), _ptr(xc), _ptr(x_hi), _ptr(x_lo),
                                              rows, plan.C,
                                              plan.Hd, plan.D, plan.blocks, float(eps), _ptr(out),
-                                             _ptr(out16), _ptr(ws), ws.numel(), _stream()))
+                                             _ptr(out16), _ptr(p_hi), _ptr(p_lo), _ptr(ws), ws.numel(),
+                                             _stream()))
     return (out, out16) if want_bf16 else out
 
 
@@ -205,14 +221,31 @@ def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, work
     """Row top-2 / column argmax of S_p = D1_p . D2_p^T without storing S.
 
     bank1 (F1,N,D), bank2 (F2,M,D); pair_index (P,2) int32 selects (a,b) per pair, default (p,p).
+    With mode=SIM_F16X3 a bank may also be the (hi, lo) fp16 pair written by l2norm_rows /
+    refiner_forward (both banks then), which skips the split pass.
     Returns dict(nn12, best12, second12 (P,N); nn21, best21 (P,M))."""
     lib = _lib.load()
-    _need_cuda(bank1, bank2, pair_index)
-    if not (bank1.is_contiguous() and bank2.is_contiguous()):
-        raise RuntimeError("descriptor banks must be contiguous")
-    want = torch.bfloat16 if mode == SIM_BF16 else torch.float32
-    if bank1.dtype != want or bank2.dtype != want:
-        raise RuntimeError(f"mode {mode} expects {want} descriptor banks")
+    presplit = isinstance(bank1, (tuple, list))
+    if presplit != isinstance(bank2, (tuple, list)):
+        raise RuntimeError("either both descriptor banks are fp16 (hi, lo) pairs or neither")
+    if presplit:
+        if mode != SIM_F16X3:
+            raise RuntimeError("fp16 (hi, lo) descriptor banks are the operand format of SIM_F16X3 only")
+        (bank1, bank1_lo), (bank2, bank2_lo) = bank1, bank2
+        _need_cuda(bank1, bank1_lo, bank2, bank2_lo)
+        for t in (bank1, bank1_lo, bank2, bank2_lo):
+            if t.dtype != torch.float16 or not t.is_contiguous():
+                raise RuntimeError("fp16 (hi, lo) descriptor banks must be contiguous fp16")
+        if bank1.shape != bank1_lo.shape or bank2.shape != bank2_lo.shape:
+            raise RuntimeError("hi and lo halves of a descriptor bank must have the same shape")
+    else:
+        bank1_lo = bank2_lo = None
+        _need_cuda(bank1, bank2, pair_index)
+        if not (bank1.is_contiguous() and bank2.is_contiguous()):
+            raise RuntimeError("descriptor banks must be contiguous")
+        want = torch.bfloat16 if mode == SIM_BF16 else torch.float32
+        if bank1.dtype != want or bank2.dtype != want:
+            raise RuntimeError(f"mode {mode} expects {want} descriptor banks")
     N, D = bank1.shape[-2], bank1.shape[-1]
     M = bank2.shape[-2]
     if pair_index is not None:
@@ -230,7 +263,8 @@ def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, work
     F2 = bank2.numel() // (M * D)
     need = lib.sslam_match_workspace_bytes(F1, F2, P, N, M, D, mode)
     ws = workspace if workspace is not None else _ws("match", need, dev)
-    _lib.check(lib.sslam_match_top2(_ptr(bank1), F1, _ptr(bank2), F2, _ptr(pair_index), int(mode), P, N, M,
+    _lib.check(lib.sslam_match_top2(_ptr(bank1), _ptr(bank1_lo), F1, _ptr(bank2), _ptr(bank2_lo), F2,
+                                    _ptr(pair_index), int(mode), P, N, M,
                                     D, _ptr(res["nn12"]), _ptr(res["best12"]), _ptr(res["second12"]),
                                     _ptr(res["nn21"]), _ptr(res["best21"]), _ptr(ws), ws.numel(),
                                     _stream()))

@@ -16,7 +16,7 @@ Two coordinate conventions:
 import torch
 
 from . import matchers, ops
-from .ops import SIM_BF16, SIM_F32
+from .ops import SIM_BF16, SIM_F32, SIM_F16X3
 
 
 class FrontEnd:
@@ -52,34 +52,57 @@ class FrontEnd:
         want16 = self.sim_mode == SIM_BF16
         o32 = out["descriptors"] if out is not None else None
         o16 = out.get("descriptors_bf16") if out is not None else None
+        # f16x3 matcher: the normalisation kernel also writes the descriptors as the fp16 (hi, lo)
+        # pair the matcher multiplies, so no split pass runs later
+        opair = None
+        if self.sim_mode == SIM_F16X3:
+            if out is not None:
+                opair = (out["descriptors_hi"], out["descriptors_lo"])
+            else:
+                D = self.refiner.output_dim
+                opair = tuple(torch.empty(B * self.K, D, dtype=torch.float16, device=kp.device) for _ in range(2))
         if fused:
-            res_d = self.refiner.forward_fused(sampled, want_bf16=want16, out=o32, out16=o16)   # MLP + L2 norm
+            res_d = self.refiner.forward_fused(sampled, want_bf16=want16, out=o32, out16=o16,
+                                               out_pair=opair)                                  # MLP + L2 norm
             self._mark(timers, "refiner_mlp")
         else:
             raw = self.refiner.forward_unnormalized(sampled)
             self._mark(timers, "refiner_mlp")
-            res_d = ops.l2norm_rows(raw, out=o32, out_bf16=o16, want_bf16=want16)
+            res_d = ops.l2norm_rows(raw, out=o32, out_bf16=o16, want_bf16=want16, pair=opair)
         d32, d16 = res_d if want16 else (res_d, None)
         if want16:
             res["descriptors_bf16"] = d16.reshape(B, self.K, -1)
+        if opair is not None:
+            res["descriptors_hi"] = opair[0].reshape(B, self.K, -1)
+            res["descriptors_lo"] = opair[1].reshape(B, self.K, -1)
         self._mark(timers, "l2norm")
         res["descriptors"] = d32.reshape(B, self.K, -1)
         res["keypoints_pixel"] = kp if self.grid == "pixel" else kp * self.patch + self.patch / 2
         return res
 
-    def bank(self, feats):
-        return feats["descriptors_bf16"] if self.sim_mode == SIM_BF16 else feats["descriptors"]
+    def bank(self, feats, start=0, stop=None):
+        """Descriptor bank (frames start:stop) in the operand format of the configured matcher."""
+        sl = slice(start, stop)
+        if self.sim_mode == SIM_BF16:
+            return feats["descriptors_bf16"][sl]
+        if self.sim_mode == SIM_F16X3 and "descriptors_hi" in feats:
+            return (feats["descriptors_hi"][sl], feats["descriptors_lo"][sl])
+        return feats["descriptors"][sl]
+
+    @staticmethod
+    def _shift(bank, k=1):
+        return tuple(t[k:] for t in bank) if isinstance(bank, tuple) else bank[k:]
 
     @torch.no_grad()
     def match_consecutive(self, feats, variant=matchers.M1, timers=None, **kw):
         """Match frame t with frame t+1 for every t of an extracted batch (P = B-1 pairs)."""
         bank = self.bank(feats)
-        F = bank.shape[0]
+        F = feats["descriptors"].shape[0]
         sc = feats["scores"]
         self._mark(timers, "begin")
-        top = ops.match_top2(bank, bank[1:], mode=self.sim_mode, num_pairs=F - 1)
+        top = ops.match_top2(bank, self._shift(bank), mode=self.sim_mode, num_pairs=F - 1)
         self._mark(timers, "match_top2")
-        out = matchers.match(bank, bank[1:], variant, num_pairs=F - 1, mode=self.sim_mode,
+        out = matchers.match(bank, self._shift(bank), variant, num_pairs=F - 1, mode=self.sim_mode,
                              scores1=sc, scores2=sc[1:], top=top, **kw)[:3]
         self._mark(timers, "match_finalize")
         return out
@@ -115,6 +138,9 @@ class FrontEnd:
                     descriptors=torch.empty(T, self.K, D, device=device))
         if self.sim_mode == SIM_BF16:
             bank["descriptors_bf16"] = torch.empty(T, self.K, D, dtype=torch.bfloat16, device=device)
+        if self.sim_mode == SIM_F16X3:
+            bank["descriptors_hi"] = torch.empty(T, self.K, D, dtype=torch.float16, device=device)
+            bank["descriptors_lo"] = torch.empty(T, self.K, D, dtype=torch.float16, device=device)
         bank["keypoints_pixel"] = bank["keypoints"]     # pixel grid: the decode output is already pixels
         return bank
 
@@ -188,9 +214,9 @@ class FrontEnd:
             # still crossing PCIe; the lists go back to the host as they are produced
             p0 = max(s - 1, 0)
             if e - 1 > p0:
-                bank = self.bank(feats)[p0:e]
+                bank = self.bank(feats, p0, e)
                 sc = feats["scores"][p0:e]
-                res = matchers.match(bank, bank[1:], variant, num_pairs=e - 1 - p0, mode=self.sim_mode,
+                res = matchers.match(bank, self._shift(bank), variant, num_pairs=e - 1 - p0, mode=self.sim_mode,
                                      scores1=sc, scores2=sc[1:], **kw)[:3]
                 for dst, src in zip(out_host, res):
                     dst[p0:e - 1].copy_(src, non_blocking=True)

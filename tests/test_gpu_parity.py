@@ -336,8 +336,10 @@ def test_abi_error_codes(dev):
     assert l.sslam_decode_topk_f32(p, 0, 1, 8, 8, 4, 2, 0.5, -1.0, p, p, p, p, 1 << 20, z) == -1  # floor
     assert "floor" in _lib.last_error()
     assert l.sslam_decode_topk_f32(p, 0, 0, 8, 8, 4, 2, 0.5, 0.1, p, p, p, p, 0, z) == 0         # empty batch
-    assert l.sslam_match_top2(p, 1, p, 1, z, 0, 1, 4, 4, 6, p, p, p, p, p, p, 1 << 20, z) == -2        # D % 4
-    assert l.sslam_match_top2(p, 1, p, 1, z, 7, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1        # dtype
+    assert l.sslam_match_top2(p, z, 1, p, z, 1, z, 0, 1, 4, 4, 6, p, p, p, p, p, p, 1 << 20, z) == -2  # D % 4
+    assert l.sslam_match_top2(p, z, 1, p, z, 1, z, 7, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1  # dtype
+    assert l.sslam_match_top2(p, p, 1, p, z, 1, z, 3, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1  # one lo only
+    assert l.sslam_match_top2(p, p, 1, p, p, 1, z, 0, 1, 4, 4, 8, p, p, p, p, p, p, 1 << 20, z) == -1  # pairs need f16x3
     assert l.sslam_launch_count() > 0
     torch.cuda.synchronize()
 

@@ -81,6 +81,33 @@ def test_f16x3_top2(n, m, d, dev):
           f"max |best-S| {np.abs(t['best12'] - S64.max(1)).max():.2e}")
 
 
+def test_f16x3_presplit_banks_equal_internal_split(dev):
+    """The fp16 (hi, lo) pair written by l2norm_rows (what the pipeline hands to the matcher) gives
+    bit-identical top-2 results to the matcher splitting the fp32 bank itself, and the pair
+    reconstructs the fp32 descriptors to 2^-22 relative."""
+    from sslam_b200 import ops
+    F, N, D = 4, 300, 256
+    g = torch.Generator(device="cpu").manual_seed(11)
+    raw = torch.randn(F, N, D, generator=g).to(dev)
+    hi = torch.empty(F, N, D, dtype=torch.float16, device=dev)
+    lo = torch.empty_like(hi)
+    d32 = ops.l2norm_rows(raw, pair=(hi, lo))
+    assert torch.equal(d32, ops.l2norm_rows(raw))
+    rec = hi.float() + lo.float() * (2.0 ** -11)
+    assert (rec - d32).abs().max().item() <= 2.0 ** -22
+    a = ops.match_top2(d32, d32[1:], mode=ops.SIM_F16X3, num_pairs=F - 1)
+    b = ops.match_top2((hi, lo), (hi[1:], lo[1:]), mode=ops.SIM_F16X3, num_pairs=F - 1)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    idx = torch.tensor([[3, 0], [1, 1]], dtype=torch.int32, device=dev)
+    a = ops.match_top2(d32, d32, pair_index=idx, mode=ops.SIM_F16X3)
+    b = ops.match_top2((hi, lo), (hi, lo), pair_index=idx, mode=ops.SIM_F16X3)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    with pytest.raises(RuntimeError):
+        ops.match_top2((hi, lo), (hi, lo), mode=ops.SIM_TF32X3)
+
+
 @pytest.mark.parametrize("n,m,d", [c for c in CASES if c[2] % 8 == 0])
 def test_bf16_top2(n, m, d, dev):
     from sslam_b200 import ops
