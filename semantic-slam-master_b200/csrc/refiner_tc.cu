@@ -399,7 +399,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   if (threadIdx.x == 0) {
     // a stage is free again when the MMAs of ALL pairs of the cluster have read it (it is refilled
     // by a multicast that writes every CTA of the same rank)
-    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)ntile); }
+    // `full` (used in the pair leader): the leader's expect_tx arrival plus one arrival of the peer's
+    // producer.  The peer's arrival carries no bytes; it is there so that EVERY producer of the
+    // cluster takes part in every use of every stage.  A producer that only waits on `empty` when it
+    // is not its turn to fetch could otherwise be overtaken by two phases of that barrier, see the
+    // old phase as incomplete again (parity aliasing) and never issue its own stage's loads:
+    // a rare deadlock (about one launch in 300 when the epilogue is the bottleneck).
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], (uint32_t)ntile); }
     mbar_init(bfull, 1);
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
     fence_barrier_init();
@@ -437,9 +443,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* st = a_stages + stage * P_STAGE_BYTES;
+          const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), leader);
           if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * P_STAGE_BYTES);
+          else mbar_arrive_cluster(full_leader);
           if (turn == ct) {
-            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), leader);
             if (ntile == 1) {
               tma_load_2d_pair(st, &tmA_hi, full_leader, kb * BK, row0);
               tma_load_2d_pair(st + BLOCK_BYTES, &tmA_lo, full_leader, kb * BK, row0);
@@ -457,6 +464,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (++turn == ntile) turn = 0;
           if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      // Producer tail: the last `empty` arrivals of every stage are tcgen05.commit multicasts from
+      // the MMA threads of ALL pairs of the cluster, delivered asynchronously into this CTA's shared
+      // memory.  Nobody would otherwise wait for them, and the cluster barrier at the end does not
+      // order them: if this CTA exited first they would land in the shared memory of whatever CTA
+      // runs here next (observed as sporadic launch failures of back-to-back GEMMs).  Drain them.
+      for (int i = 0; i < P_STAGES; ++i) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -577,10 +593,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         const int col0 = half * 64 + un * UNIT;         // first column of this unit inside the tile
         const int gc0 = col_base + col0;                // ... and in the output (warp-uniform)
         // (one unit ahead only: a deeper prefetch makes ptxas spill, and registers that are the
-        // target of an in-flight tcgen05.ld must never be spilled or moved before tcgen05.wait::ld —
-        // ptxas does not know they are still being written; the Makefile builds with
-        // --warn-on-spills.  Requesting the whole slab up front and giving up the accumulator
-        // pipelining instead measured 5 % slower.)
+        // target of an in-flight tcgen05.ld should not be spilled before tcgen05.wait::ld; the
+        // Makefile builds with --warn-on-spills.  Requesting the whole slab up front and giving up
+        // the accumulator pipelining instead measured 5 % slower.)
         uint4 rh[2], rl[2];
         if (RES) {
           rh[0] = nh[0]; rh[1] = nh[1]; rl[0] = nl[0]; rl[1] = nl[1];
@@ -973,3 +988,9 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
 // wait_tempty, wait_weights; epilogue warp 2: total, wait_tfull, wait_store, tiles}, 8 int64 per CTA)
 // are written to buf (device) while buf != NULL.
 extern "C" void sslam_debug_gemm_stalls(long long* buf) { sslam::g_gemm_dbg = buf; }
+
+// Debug aid for tools/: host-mapped buffer (device pointer) that receives watchdog records of this
+// translation unit's kernels; see tc_common.cuh.
+extern "C" int sslam_debug_watchdog_gemm(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(sslam::tc::g_watchdog_buf, &buf, sizeof(buf));
+}

@@ -58,6 +58,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // Bounded wait: a protocol bug traps after ~2 s (launch failure reported to the host) instead of
 // hanging the GPU.
+// Debug aid: when set (tools only), a timed-out wait records {block, thread, barrier address, parity}
+// in this host-mapped buffer before trapping.  One copy per translation unit.
+static __device__ unsigned long long* g_watchdog_buf = nullptr;
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
@@ -77,7 +81,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) __trap();
+      else if (now - t0 > (threadIdx.x < 64 ? 1500000000ull : 2000000000ull)) {   // control warps report first
+        if (g_watchdog_buf) {
+          const bool ctl = threadIdx.x < 64;               // producer / MMA warps first
+          const unsigned long long slot = atomicAdd(g_watchdog_buf + (ctl ? 1 : 0), 1ull);
+          if (slot < (ctl ? 30ull : 32ull)) {
+            uint32_t crank;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+            g_watchdog_buf[(ctl ? 2 : 32) + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 36) |
+                                       ((unsigned long long)(crank & 15) << 32) | ((unsigned long long)(addr & 0xffffff) << 4) |
+                                       (parity & 1);
+          }
+          __threadfence_system();
+        }
+        __trap();
+      }
     }
   }
 }
