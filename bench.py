@@ -37,11 +37,12 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 _REAL_STDOUT = None
-# dram__bytes_read.sum + dram__bytes_write.sum per gemm_f16x3 launch (131072 rows), averaged over the
+# dram__bytes_read.sum + dram__bytes_write.sum of the refiner GEMM, per activation row, averaged over the
 # six launches of one refiner call in the committed `ncu --set full` capture
-# (profiles/r1_all_kernels_full.txt: 3 x 362 MB plain, 2 x 582 MB with residual, 1 x 300 MB output
-# projection); the algorithmic figure for the same launches is 458 MB (pair in + pair out [+ residual]).
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 425e6
+# (profiles/r1b_all_kernels_full.txt, 614 400 rows: 1.86 / 1.88 / 2.84 / 1.87 / 2.83 / 1.54 GB); the
+# algorithmic figure for the same launches is 3 072 B per row (pair in + pair out) and 4 608 B with
+# the residual.
+NCU_GEMM_DRAM_BYTES_PER_ROW = 3475.0
 
 
 def emit(line):
@@ -66,7 +67,7 @@ def parse():
     ap.add_argument("--mode", default="auto", choices=["auto", "f32", "tf32x3", "f16x3", "bf16"])
     ap.add_argument("--chunk", type=int, default=300, help="frames per extraction launch group (device-resident arm)")
     ap.add_argument("--e2e-chunk", type=int, default=50, help="frames per host->device staging buffer (e2e arm)")
-    ap.add_argument("--cpu-sample-frames", type=int, default=301)
+    ap.add_argument("--cpu-sample-frames", type=int, default=601)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
@@ -377,7 +378,8 @@ def run_b200(a):
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
     # dram bytes per launch from the committed `ncu --set full` capture (profiles/), where available
-    ncu_traffic = {"gemm_f16x3": NCU_GEMM_DRAM_BYTES_PER_LAUNCH * (a.chunk / 64.0) if NCU_GEMM_DRAM_BYTES_PER_LAUNCH else None}
+    ncu_traffic = {"gemm_f16x3": NCU_GEMM_DRAM_BYTES_PER_ROW * rows / (dk["launches_per_step"] / 6.0)
+                   if dom == "gemm_f16x3" else None}
     tf32_note = ("fp32 accuracy costs three 16-bit MMAs per product (fp16 hi/lo split), so the ceiling of "
                  "this fraction is 1/3 = 0.333 (1/6 for the tf32x3 variant)")
     if work.get(dom, ("", 0))[0] == "tensor":

@@ -390,6 +390,24 @@ def test_host_streaming_pipeline_matches_device_pipeline(dev):
         assert torch.equal(hs, pscores.cpu()), chunk
 
 
+def test_refiner_back_to_back_launches_are_stable(dev):
+    """Regression test for the cluster pipeline of the refiner GEMM: 400 forwards of a 50-frame chunk
+    (102 400 rows, the e2e staging size) enqueued back to back must all complete and give bit-identical
+    descriptors.  (A producer that could be overtaken by two phases of a stage's `empty` barrier used
+    to deadlock about one launch in 300 in the residual layers.)"""
+    from models.descriptor_refiner import DescriptorRefiner
+    torch.manual_seed(0)
+    m = DescriptorRefiner(384, 384, 256, 4).to(dev).eval()
+    x = torch.randn(1, 102400, 384, device=dev)
+    with torch.no_grad():
+        ref = m.forward_fused(x).clone()
+        for it in range(400):
+            y = m.forward_fused(x)
+            if it % 100 == 99:
+                assert torch.equal(y, ref), it
+    torch.cuda.synchronize()
+
+
 def test_empty_and_degenerate_shapes(dev):
     """Empty batches / zero keypoints / tiny maps go through the C ABI without launching."""
     from sslam_b200 import ops
