@@ -298,7 +298,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // keep the epilogue under the MMA time of a tile.
 template <int MODE> struct RCfg;
 template <> struct RCfg<SSLAM_SIM_F16X3> {
-  static constexpr int TERMS = 2, B_BK = 32, B_SWZ = 64, B_STAGES = 4, ACC_COLS = 2 * BN, TMEM_COLS = 512;
+  static constexpr int TERMS = 2, B_BK = 64, B_SWZ = 128, B_STAGES = 4, ACC_COLS = 2 * BN, TMEM_COLS = 512;
   static constexpr uint32_t FMT = FMT_F16;
   static constexpr float CROSS_SCALE = 1.0f / 2048.0f;
 };
@@ -316,24 +316,24 @@ template <int MODE>
 struct RSmem {
   using C = RCfg<MODE>;
   static constexpr int A_BYTES = R_MAX_KB * C::TERMS * BLOCK_BYTES;
-  static constexpr int B_TILE = BN * C::B_BK * 2;                    // one term of one stage
-  static constexpr int B_STAGE = C::TERMS * B_TILE;                  // hi then lo: a 256-row operand
+  static constexpr int B_TILE = (BN / 2) * C::B_BK * 2;              // one term of one stage: this CTA's 64 of the tile's 128 rows
+  static constexpr int B_STAGE = C::TERMS * B_TILE;                  // hi then lo
   static constexpr int OPERANDS = A_BYTES + C::B_STAGES * B_STAGE;
   static constexpr int COLPART = 2 * 4 * BN * 8;                     // [acc][lane quarter][col] u64
   static constexpr int TRANSP = R_EPI_WARPS * 32 * R_UNIT * 4;       // [warp][32 rows][16] fp32, swizzled
   static constexpr int ROWMERGE = 2 * BM * 3 * 4;                    // [item parity][row][best, idx, second]
   static constexpr int BARS = (2 * C::B_STAGES + 2 * R_MAX_KB + 4) * 8 + 16;
+  static_assert(C::B_BK == 64, "the pair kernel stages whole 64-element k-blocks");
   static constexpr int TOTAL = OPERANDS + COLPART + TRANSP + ROWMERGE + BARS + 1024;
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(R_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(R_THREADS, 1)
 match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                  const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                  TcParams p) {
   using C = RCfg<MODE>;
   using L = RSmem<MODE>;
-  constexpr int SUBS = 64 / C::B_BK;                                  // B stages per A k-block
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   unsigned char* a_res = smem;
@@ -351,66 +351,88 @@ match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // CTA pair (cta_group::2): the two CTAs own two adjacent 128-row strips of the SAME pair and share
+  // every MMA (M = 256); each holds its own strip resident and HALF of every B tile (64 of its 128
+  // rows), so the B stream per SM — shared-memory writes, L2 traffic and, for a given number of
+  // bytes in flight, pipeline depth — is half of what a single CTA needs.  Work item of the pair =
+  // (pair of sets, strip pair); rank 0 issues the MMAs.
+  const uint32_t rank = cluster_ctarank();
   const int strips = (p.N + BM - 1) / BM;
-  const int nitems = strips * p.P;
+  const int strips2 = (strips + 1) / 2;
+  const int nitems = strips2 * p.P;
+  const int pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int ntile = (p.M + BN - 1) / BN;
-  const int nsub = (p.D + C::B_BK - 1) / C::B_BK;                     // B stages per tile
+  const int nkb = (p.D + 63) / 64;                                    // k-blocks = B stages per tile
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int k = 0; k < R_MAX_KB; ++k) { mbar_init(&afull[k], 1); mbar_init(&aempty[k], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], R_EPI_WARPS); }
+    // full / afull live in the leader: its expect_tx arrival + one arrival of the peer's producer, so
+    // that both producers take part in every use (no producer can be overtaken by two phases)
+    for (int s = 0; s < C::B_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+    for (int k = 0; k < R_MAX_KB; ++k) { mbar_init(&afull[k], 2); mbar_init(&aempty[k], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * R_EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 1) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
+    // ================================ TMA producer (both CTAs) ================================
     if (elect_one()) {
       prefetch_tensormap(&tmA_hi); prefetch_tensormap(&tmB_hi);
       if (C::TERMS == 2) { prefetch_tensormap(&tmA_lo); prefetch_tensormap(&tmB_lo); }
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-        const int pair = item / strips;
+      for (int item = pair_id; item < nitems; item += npairs, ++it) {
+        const int pair = item / strips2;
         int ia = pair, ib = pair;
         if (p.pair_index) { ia = p.pair_index[2 * pair]; ib = p.pair_index[2 * pair + 1]; }
-        const int a_row = ia * p.N + (item - pair * strips) * BM;
-        const int b_row0 = ib * p.M;
+        // an odd strip count leaves the last item of a pair with one real strip: the other CTA runs
+        // the same loop on rows past the set (masked in the epilogue)
+        const int a_row = ia * p.N + (2 * (item - pair * strips2) + (int)rank) * BM;
+        const int b_row0 = ib * p.M + (int)rank * (BN / 2);
         for (int ct = 0; ct < ntile; ++ct) {
-          for (int sb = 0; sb < nsub; ++sb) {
-            if (ct == 0 && (sb % SUBS) == 0) {                  // this item's A k-block
-              const int kb = sb / SUBS;
+          for (int kb = 0; kb < nkb; ++kb) {
+            if (ct == 0) {                                      // this item's A k-block (own strip)
               mbar_wait(&aempty[kb], (uint32_t)(it & 1) ^ 1u);  // last tile of the previous item done with it
-              mbar_arrive_expect_tx(&afull[kb], C::TERMS * BLOCK_BYTES);
-              tma_load_2d(a_res + (kb * C::TERMS) * BLOCK_BYTES, &tmA_hi, &afull[kb], kb * 64, a_row);
+              const uint32_t afull_leader = mapa_u32(smem_u32(&afull[kb]), 0);
+              if (rank == 0) mbar_arrive_expect_tx(&afull[kb], 2u * C::TERMS * BLOCK_BYTES);
+              else mbar_arrive_cluster(afull_leader);
+              tma_load_2d_pair(a_res + (kb * C::TERMS) * BLOCK_BYTES, &tmA_hi, afull_leader, kb * 64, a_row);
               if (C::TERMS == 2)
-                tma_load_2d(a_res + (kb * C::TERMS + 1) * BLOCK_BYTES, &tmA_lo, &afull[kb], kb * 64, a_row);
+                tma_load_2d_pair(a_res + (kb * C::TERMS + 1) * BLOCK_BYTES, &tmA_lo, afull_leader, kb * 64, a_row);
             }
             mbar_wait(&empty[stage], phase ^ 1);
             unsigned char* st = b_stages + stage * L::B_STAGE;
-            mbar_arrive_expect_tx(&full[stage], L::B_STAGE);
-            tma_load_2d(st, &tmB_hi, &full[stage], sb * C::B_BK, b_row0 + ct * BN);
-            if (C::TERMS == 2) tma_load_2d(st + L::B_TILE, &tmB_lo, &full[stage], sb * C::B_BK, b_row0 + ct * BN);
+            const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * L::B_STAGE);
+            else mbar_arrive_cluster(full_leader);
+            tma_load_2d_pair(st, &tmB_hi, full_leader, kb * 64, b_row0 + ct * BN);
+            if (C::TERMS == 2) tma_load_2d_pair(st + L::B_TILE, &tmB_lo, full_leader, kb * 64, b_row0 + ct * BN);
             if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
           }
         }
       }
+      // producer tail: the last empty / aempty arrivals are asynchronous tensor-core commits into this
+      // CTA's shared memory; drain them before the CTA may exit
+      for (int i = 0; i < C::B_STAGES; ++i) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (it > 0)
+        for (int kb = 0; kb < nkb; ++kb) mbar_wait(&aempty[kb], (uint32_t)(it & 1) ^ 1u);
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (elect_one()) {
-      const uint32_t idesc = make_instr_desc(C::FMT, BM, BN);
-      const uint32_t idesc_cat = make_instr_desc(C::FMT, BM, 2 * BN);
+    // ================================ MMA issuer (leader CTA) ================================
+    if (rank == 0 && elect_one()) {
+      const uint32_t idesc = make_instr_desc(C::FMT, 2 * BM, BN);      // M = 256 across the pair
       int stage = 0; uint32_t phase = 0;
       int tc = 0, it = 0;
       const bool dbg_on = p.dbg != nullptr;
       long long w_full = 0, w_tempty = 0, w_afull = 0, t_begin = clock64(), tq = 0;
-      for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
+      for (int item = pair_id; item < nitems; item += npairs, ++it) {
         for (int ct = 0; ct < ntile; ++ct, ++tc) {
           const int acc = tc & 1;
           if (dbg_on) tq = clock64();
@@ -418,34 +440,33 @@ match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
           if (dbg_on) w_tempty += clock64() - tq;
           tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + acc * C::ACC_COLS;
-          for (int sb = 0; sb < nsub; ++sb) {
-            const int kb = sb / SUBS, h = sb % SUBS;
+          for (int kb = 0; kb < nkb; ++kb) {
             if (dbg_on) tq = clock64();
-            if (ct == 0 && h == 0) mbar_wait(&afull[kb], (uint32_t)(it & 1));
+            if (ct == 0) mbar_wait(&afull[kb], (uint32_t)(it & 1));
             if (dbg_on) w_afull += clock64() - tq;
             if (dbg_on) tq = clock64();
             mbar_wait(&full[stage], phase);
             if (dbg_on) w_full += clock64() - tq;
             tcgen05_fence_after();
-            const uint32_t sa = smem_u32(a_res + (kb * C::TERMS) * BLOCK_BYTES) + h * C::B_BK * 2;
-            const uint32_t sb_addr = smem_u32(b_stages + stage * L::B_STAGE);
+            const uint32_t sa = smem_u32(a_res + (kb * C::TERMS) * BLOCK_BYTES);
+            const uint32_t sb = smem_u32(b_stages + stage * L::B_STAGE);
             const uint64_t a_hi = make_smem_desc_sw128(sa);
             const uint64_t a_lo = make_smem_desc_sw128(sa + BLOCK_BYTES);
-            const uint64_t b_cat = C::B_SWZ == 64 ? make_smem_desc_sw64(sb_addr) : make_smem_desc_sw128(sb_addr);
+            const uint64_t b_hi = make_smem_desc_sw128(sb);
+            const uint64_t b_lo = make_smem_desc_sw128(sb + L::B_TILE);
 #pragma unroll
-            for (int k = 0; k < C::B_BK / 16; ++k) {            // 16 elements = 32 bytes of K per instruction
+            for (int k = 0; k < 4; ++k) {                       // 16 elements = 32 bytes of K per instruction
               const uint64_t adv = (uint64_t)(k * 32 >> 4);
-              const uint32_t first = (sb | k) ? 1u : 0u;
+              const uint32_t first = (kb | k) ? 1u : 0u;
               if (C::TERMS == 2) {
-                umma_ss<false>(tmem_d, a_hi + adv, b_cat + adv, idesc_cat, first);   // hi.hi | hi.lo
-                umma_ss<false>(tmem_d + BN, a_lo + adv, b_cat + adv, idesc, 1u);     // + lo.hi
-              } else {
-                umma_ss<false>(tmem_d, a_hi + adv, b_cat + adv, idesc, first);
+                umma_ss_pair(tmem_d + BN, a_lo + adv, b_hi + adv, idesc, first);
+                umma_ss_pair(tmem_d + BN, a_hi + adv, b_lo + adv, idesc, 1u);
               }
+              umma_ss_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
             }
-            tcgen05_commit(&empty[stage]);
-            if (ct == ntile - 1 && (h == SUBS - 1 || sb == nsub - 1)) tcgen05_commit(&aempty[kb]);
-            if (sb == nsub - 1) tcgen05_commit(&tfull[acc]);
+            tcgen05_commit_pair(&empty[stage], 3);
+            if (ct == ntile - 1) tcgen05_commit_pair(&aempty[kb], 3);
+            if (kb == nkb - 1) tcgen05_commit_pair(&tfull[acc], 3);
             if (++stage == C::B_STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -465,9 +486,11 @@ match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     const int sc = lane & 15, srh = lane >> 4;                  // column scan: column / row parity
     const float NEG_INF = __int_as_float(0xff800000);
     int tc = 0, it = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x, ++it) {
-      const int pair = item / strips;
-      const int row0 = (item - pair * strips) * BM;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), 0);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), 0);
+    for (int item = pair_id; item < nitems; item += npairs, ++it) {
+      const int pair = item / strips2;
+      const int row0 = (2 * (item - pair * strips2) + (int)rank) * BM;
       const int grow = row0 + q * 32 + lane;
       const bool row_ok = grow < p.N;
       int nvalid = p.N - (row0 + q * 32);
@@ -579,7 +602,7 @@ match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // accumulator fully read: hand it back to the MMA warp
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
         // merge the four lane quarters' column results and publish
         named_bar_sync(1, 32 * R_EPI_WARPS);
         if (et < BN) {
@@ -607,8 +630,8 @@ match_res_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
 // fp32 -> (tf32 hi, tf32 lo) split of a descriptor bank
@@ -735,8 +758,9 @@ static int launch_res(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CU
                                           L::TOTAL));
     configured.store(true);
   }
-  const int items = ((tp.N + BM - 1) / BM) * tp.P;
-  const int grid = items < num_sms() ? items : num_sms();          // persistent: one CTA per SM
+  const int items = ((((tp.N + BM - 1) / BM) + 1) / 2) * tp.P;      // (pair of sets, strip pair)
+  const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;
+  const int grid = 2 * pairs;                                      // persistent: one CTA pair per TPC
   SSLAM_LAUNCH(KK_MATCH_TC, stream,
                match_res_kernel<MODE><<<grid, R_THREADS, L::TOTAL, stream>>>(a_hi, a_lo, b_hi, b_lo, tp));
   return SSLAM_OK;
@@ -755,7 +779,7 @@ int match_top2_tc(const void* bank1, const void* bank1_lo, int F1, const void* b
   if (dtype == SSLAM_SIM_BF16) {
     SSLAM_REQUIRE(D % 8 == 0, SSLAM_EUNSUPPORTED, "match(bf16): D=%d must be a multiple of 8", D);
     if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
-    if ((rc = make_tensor_map_2d(&b_hi, bank2, (uint64_t)F2 * M, D, BN, 64, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, bank2, (uint64_t)F2 * M, D, BN / 2, 64, 2))) return rc;   // half tile per CTA
     a_lo = a_hi; b_lo = b_hi;
     return launch_res<SSLAM_SIM_BF16>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
@@ -768,8 +792,8 @@ int match_top2_tc(const void* bank1, const void* bank1_lo, int F1, const void* b
     const uint64_t rows2p = (uint64_t)F2 * M;
     if ((rc = make_tensor_map_2d(&a_hi, bank1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
     if ((rc = make_tensor_map_2d(&a_lo, bank1_lo, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
-    if ((rc = make_tensor_map_2d(&b_hi, bank2, rows2p, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
-    if ((rc = make_tensor_map_2d(&b_lo, bank2_lo, rows2p, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, bank2, rows2p, D, BN / 2, 64, 2))) return rc;        // half tile per CTA
+    if ((rc = make_tensor_map_2d(&b_lo, bank2_lo, rows2p, D, BN / 2, 64, 2))) return rc;
     return launch_res<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
   SSLAM_REQUIRE(ws_extra_bytes >= match_tc_extra_workspace(P, N, M, D, dtype, F1, F2), SSLAM_EWORKSPACE,
@@ -813,8 +837,8 @@ int match_top2_tc(const void* bank1, const void* bank1_lo, int F1, const void* b
     // swizzled stages
     if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
     if ((rc = make_tensor_map_2d(&a_lo, l1, (uint64_t)F1 * N, D, BM, 64, 2))) return rc;
-    if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
-    if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN, RCfg<SSLAM_SIM_F16X3>::B_BK, 2, 64))) return rc;
+    if ((rc = make_tensor_map_2d(&b_hi, h2, rows2, D, BN / 2, 64, 2))) return rc;            // half tile per CTA
+    if ((rc = make_tensor_map_2d(&b_lo, l2, rows2, D, BN / 2, 64, 2))) return rc;
     return launch_res<SSLAM_SIM_F16X3>(a_hi, a_lo, b_hi, b_lo, tp, stream);
   }
   if ((rc = make_tensor_map_2d(&a_hi, h1, (uint64_t)F1 * N, D, BM, 32, 4))) return rc;
