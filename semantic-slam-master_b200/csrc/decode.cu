@@ -307,19 +307,18 @@ __global__ void __launch_bounds__(256) decode_scan_vec_kernel(DecodeParams p, in
             cv[c] = cwin[(u + WIN - R) % WIN][c];
             if (out_lane && (cv[c] == m) && (cv[c] > min_keep)) mask |= 1u << c;
           }
-          if (mask) {
-            // local maxima are sparse (~4 % of the pixels): the few lanes that found one append it
-            // to the CTA's staging list themselves (order in the list is irrelevant, K2 sorts keys)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              if ((mask >> c) & 1u) {
-                const u32 lin = (u32)(yo * W + x + c);
-                const u64 key = ((u64)__float_as_uint(cv[c]) << 32) | (u64)(0xffffffffu - lin);
-                const u32 pos = atomicAdd(&scount, 1u);
-                if (pos < (u32)CAP) sbuf[pos] = key;
-                else cand[atomicAdd(&hdr->cand_count, 1u)] = key;   // staging list full (plateau maps)
-              }
-            }
+          // local maxima are sparse (~4 % of the pixels) and a lane rarely holds more than one: the
+          // lanes that found any append them themselves, one loop trip per maximum (order in the
+          // list is irrelevant, K2 sorts keys)
+          while (mask) {
+            const int c = __ffs((int)mask) - 1;
+            mask &= mask - 1;
+            const float val = c == 0 ? cv[0] : c == 1 ? cv[1] : c == 2 ? cv[2] : cv[3];
+            const u32 lin = (u32)(yo * W + x + c);
+            const u64 key = ((u64)__float_as_uint(val) << 32) | (u64)(0xffffffffu - lin);
+            const u32 pos = atomicAdd(&scount, 1u);
+            if (pos < (u32)CAP) sbuf[pos] = key;
+            else cand[atomicAdd(&hdr->cand_count, 1u)] = key;   // staging list full (plateau maps)
           }
         }
       }
