@@ -34,15 +34,17 @@ struct TapGeom {
 };
 
 __device__ __forceinline__ TapGeom tap_geometry(float x, float y, int H, int W, int coords) {
+  // divisions by 16 and by 2 are exact scalings: multiplying by 2^-4 / 2^-1 gives the same bits as
+  // the reference's divisions (no underflow at these magnitudes) without the IEEE division sequence
   if (coords == 1) {                                    // pixel_to_patch: (p - 8) / 16  (:177)
-    x = __fdiv_rn(__fsub_rn(x, 8.0f), 16.0f);
-    y = __fdiv_rn(__fsub_rn(y, 8.0f), 16.0f);
+    x = __fmul_rn(__fsub_rn(x, 8.0f), 0.0625f);
+    y = __fmul_rn(__fsub_rn(y, 8.0f), 0.0625f);
   }
   const float wm1 = (float)(W - 1), hm1 = (float)(H - 1);
   float nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, x), wm1), 1.0f);
   float ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, y), hm1), 1.0f);
-  float ix = __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.0f), 2.0f), wm1);
-  float iy = __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.0f), 2.0f), hm1);
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.0f), 0.5f), wm1);
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.0f), 0.5f), hm1);
   float x0 = floorf(ix), y0 = floorf(iy);
   float x1 = __fadd_rn(x0, 1.0f), y1 = __fadd_rn(y0, 1.0f);
   float wx0 = __fsub_rn(x1, ix), wx1 = __fsub_rn(ix, x0);
