@@ -1,33 +1,32 @@
 // Tensor-core similarity with the top-2 / argmax epilogue fused in: tcgen05.mma accumulating in
-// TMEM, operands staged by TMA into 128B-swizzled shared memory, mbarrier pipelines, no similarity
-// matrix in HBM.
+// TMEM, operands staged by TMA into swizzled shared memory, mbarrier pipelines, no similarity
+// matrix in HBM.  Two kernels:
 //
-//   SSLAM_SIM_BF16   : S = A.B^T on bf16 copies (kind::f16), fp32 accumulate.
-//   SSLAM_SIM_TF32X3 : "fp32 mode".  Each fp32 operand x is split into hi = tf32(x) and
-//                      lo = tf32(x - hi) (both round-to-nearest, so hi + lo carries ~22 mantissa
-//                      bits) and S = Ah.Bh + Ah.Bl + Al.Bh with kind::tf32, fp32 accumulate in TMEM.
-//                      The dropped Al.Bl term is <= 2^-22 |a||b|.  The tensor core adds into its fp32
-//                      accumulator with truncation, so the 2^-11-sized cross terms are kept in their
-//                      OWN TMEM accumulator (64 of the 96 MMAs per tile) and added to the Ah.Bh
-//                      accumulator once, in the epilogue, with a round-to-nearest FADD; measured on
-//                      B200 this takes the error from ~3e-6 to < 1e-6.  Against the exact-mode kernel
-//                      decisions are identical except for similarity near-ties (< 1e-6), which the
-//                      parity tests count.
+//   match_res_kernel<F16X3 | BF16>  (further down) — the production path.  CTA pairs (cta_group::2,
+//       M = 256): each CTA keeps its 128-row strip of set 1 resident in shared memory and half of
+//       every streamed B tile; rank 0 issues the MMAs of both.
+//         SSLAM_SIM_F16X3 : "fp32 mode".  x ~= hi + lo * 2^-11 with hi, lo fp16 (22 significant
+//                           bits); S = Ah.Bh + 2^-11 (Ah.Bl + Al.Bh) on kind::f16 MMAs.
+//         SSLAM_SIM_BF16  : S = A.B^T on bf16 copies, fp32 accumulate.
+//   match_tc_kernel<TF32X3>  (directly below) — the streaming single-CTA kernel, kept as the
+//       cross-check of f16x3: hi = tf32(x), lo = tf32(x - hi), kind::tf32 (half the tensor rate,
+//       twice the operand bytes).
 //
-// Persistent kernel, one CTA per SM.  A work item is one 128-row strip of one pair (items blockIdx,
-// +gridDim, ...); inside an item the CTA walks the column tiles (128 wide) of the pair:
-//   warp 0      TMA producer   : per k-block (128 bytes of K) loads the A and B tiles of every term
-//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma; tcgen05.commit releases the
-//                                smem stage and, after the last k-block, publishes the accumulator
-//   warps 2..5  epilogue       : tcgen05.ld the 128x128 fp32 tile (thread = row), update the row's
-//                                running (best, index, second); for the column argmax each warp
-//                                transposes its 32x32 chunk through a padded smem tile so that lane j
-//                                scans column j over the warp's 32 rows (no cross-lane reductions:
-//                                redux.sync turned out to cost ~16k cycles per tile), then the four
-//                                warps' results are merged and published across strips with a 64-bit
-//                                atomicMax on (ordered value << 32 | ~row)
-// Two accumulator sets (bf16: 2 x 128 TMEM columns; tf32x3: 2 x (128 + 128)) let the epilogue of
-// tile t overlap the MMAs of tile t+1.
+// In both split modes the tensor core adds into its fp32 accumulator with truncation, so the
+// 2^-11-sized cross terms are kept in their OWN TMEM accumulator and added to the Ah.Bh accumulator
+// once, in the epilogue, with a round-to-nearest FMA; measured on B200 this takes the error from
+// ~3e-6 to < 1e-6.  The dropped Al.Bl term is <= 2^-22 |a||b|.  Against the exact-mode kernel
+// (match_f32.cu) decisions are identical except for similarity near-ties (< 1e-6), which the parity
+// tests count.
+//
+// Roles in both kernels: warp 0 TMA producer, warp 1 MMA issuer (one elected thread), the remaining
+// warps epilogue (thread = row: running (best, index, second) per row; column argmax per 32-row
+// chunk merged across strips by a 64-bit atomicMax on (ordered value << 32 | ~row)).  Two TMEM
+// accumulator sets let the epilogue of tile t overlap the MMAs of tile t+1.
+//
+// match_tc_kernel: a work item is one 128-row strip of one pair; the CTA walks the 128-wide column
+// tiles, loading the A and B tiles of every term per k-block; four epilogue warps transpose each
+// 32x32 chunk through padded shared memory for the column scan (redux.sync cost ~16k cycles/tile).
 #include "tc_common.cuh"
 
 #include <mutex>

@@ -26,9 +26,12 @@
 //     and its epilogue applies the two per-row scalars; those (mu_r, rho_r) are produced for free by
 //     the epilogue of the GEMM that wrote h (row sums of v and v^2 while storing).
 //
-// Persistent kernel, one CTA per SM: each CTA walks 128-row strips (blockIdx, +gridDim, ...) and,
-// inside a strip, the N/128 column tiles of the layer, so TMEM/barrier set-up is paid once and the
-// store epilogue of a strip overlaps the MMAs of the next.
+// Two kernels.  gemm_pair_kernel (further down) is the production path for K <= 384, N <= 512:
+// weight-stationary CTA pairs (cta_group::2, M = 256), the pairs of the column tiles of one strip
+// set forming a cluster that multicasts the activation tiles.  gemm_f16x3_kernel (directly below)
+// is the general single-CTA fallback: persistent, one CTA per SM, each CTA walks 128-row strips
+// (blockIdx, +gridDim, ...) and, inside a strip, the N/128 column tiles of the layer, streaming
+// both operands.
 #include "tc_common.cuh"
 
 namespace sslam {
