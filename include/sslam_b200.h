@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SSLAM_ABI_VERSION 2
+#define SSLAM_ABI_VERSION 3
 
 enum {
   SSLAM_OK = 0,
@@ -62,7 +62,10 @@ enum {
 
 /* acceptance rule for sslam_match_finalize; params[] meaning per variant */
 enum {
-  SSLAM_MATCH_M1 = 1, /* visualize_matches.py:102-124      params[0] = ratio_thresh              */
+  SSLAM_MATCH_M1 = 1, /* visualize_matches.py:102-124      params[0] = ratio_thresh, params[1] = 0:
+                         compare `sim > second*ratio` in fp32 (NumPy >= 2 scalar promotion, the
+                         behaviour the golden fixtures were written under), 1: in double (NumPy < 2,
+                         which the reference's requirements.txt:1 pins)                           */
   SSLAM_MATCH_M2 = 2, /* visualize_matches_sequence.py:106-197  params = {saliency_weight,
                          min_saliency, min_descriptor_sim, min_intensity, 1 - saliency_weight
                          (rounded to fp32 by the caller, as Python computes it in double)}       */
@@ -187,7 +190,8 @@ int sslam_match_top2(const void* bank1, const void* bank1_lo, int F1, const void
  *   scores1/scores2 (saliency per keypoint, banks [*,N] / [*,M]) are required for M2;
  *   inten1/inten2 optional (M2).  They are indexed by the same (a,b) as the descriptor banks.
  */
-int sslam_match_finalize(int variant, const float* params /* host, 8 floats */,
+int sslam_match_finalize(int variant, const double* params /* host, 8 doubles; rounded to fp32
+                         where the reference compares in fp32 */,
                          const int32_t* pair_index, int P, int N, int M, const int32_t* nn12,
                          const float* best12, const float* second12, const int32_t* nn21,
                          const float* best21, const float* scores1, const float* scores2,

@@ -43,10 +43,15 @@ def similarity_top2(desc1, desc2):
     return nn12, best12, second12, nn21, best21, S
 
 
-def match_m1(desc1, desc2, ratio_thresh=0.8, top=None):
+def match_m1(desc1, desc2, ratio_thresh=0.8, top=None, promotion="nep50"):
     """``MatchVisualizer.find_matches`` (visualize_matches.py:102-124): list of (i, j, sim),
     ascending i; mutual and ``sim > second_best * ratio_thresh`` where the best column is
-    replaced by -1 before taking the second maximum (:117-119)."""
+    replaced by -1 before taking the second maximum (:117-119).
+
+    ``promotion``: the comparison at :121 multiplies a NumPy fp32 *scalar* by a Python float.  NumPy >= 2
+    (NEP 50; this container, and what the golden fixtures were written under) casts the float to fp32
+    ("nep50"); NumPy < 2, which the reference's requirements.txt:1 pins, promotes the product to
+    float64 ("legacy").  Rows within one fp32 ulp of the threshold can differ between the two."""
     nn12, best12, second12, nn21, _, _ = top if top is not None else similarity_top2(desc1, desc2)
     out = []
     rt = F32(ratio_thresh)
@@ -54,7 +59,11 @@ def match_m1(desc1, desc2, ratio_thresh=0.8, top=None):
         j = int(nn12[i])
         if nn21[j] == i:                                             # :114
             second = max(F32(second12[i]), F32(-1))                  # :118-119
-            if best12[i] > F32(second * rt):                         # :121
+            if promotion == "legacy":
+                ok = float(best12[i]) > float(second) * float(ratio_thresh)
+            else:
+                ok = best12[i] > F32(second * rt)
+            if ok:                                                   # :121
                 out.append((i, j, F32(best12[i])))
     return out
 

@@ -217,6 +217,7 @@ __global__ void unpack_cols_kernel(const u64* __restrict__ keys, long long total
 struct FinalizeParams {
   int variant;
   float prm[8];
+  double prm_d[2];                                          // M1 with legacy promotion: ratio as a double
   const int32_t* pair_index;
   int P, N, M;
   const int32_t* nn12; const float* best12; const float* second12;
@@ -235,6 +236,9 @@ __device__ __forceinline__ bool accept_row(const FinalizeParams& f, int pair, in
     case SSLAM_MATCH_M1: {                                 // visualize_matches.py:114-122
       float second = fmaxf(f.second12[ro], -1.0f);         // best column overwritten with -1 (:118)
       score = best;
+      // `sim > second_best * ratio_thresh` on NumPy scalars: fp32 under NumPy 2 (NEP 50, the Python float
+      // is cast to fp32), double under the NumPy < 2 the reference pins (requirements.txt:1)
+      if (f.prm[1] != 0.f) return mutual && ((double)best > __dmul_rn((double)second, f.prm_d[0]));
       return mutual && (best > __fmul_rn(second, f.prm[0]));
     }
     case SSLAM_MATCH_M2: {                                 // visualize_matches_sequence.py:158-192
@@ -376,7 +380,7 @@ extern "C" int sslam_match_top2(const void* bank1, const void* bank1_lo, int F1,
   return SSLAM_OK;
 }
 
-extern "C" int sslam_match_finalize(int variant, const float* params, const int32_t* pair_index,
+extern "C" int sslam_match_finalize(int variant, const double* params, const int32_t* pair_index,
                                     int P, int N, int M, const int32_t* nn12, const float* best12,
                                     const float* second12, const int32_t* nn21, const float* best21,
                                     const float* scores1, const float* scores2, const float* inten1,
@@ -395,7 +399,8 @@ extern "C" int sslam_match_finalize(int variant, const float* params, const int3
                 "finalize: M2 needs saliency scores");
   FinalizeParams f;
   f.variant = variant;
-  for (int i = 0; i < 8; ++i) f.prm[i] = params[i];
+  for (int i = 0; i < 8; ++i) f.prm[i] = (float)params[i];
+  f.prm_d[0] = params[0]; f.prm_d[1] = params[1];
   f.pair_index = pair_index; f.P = P; f.N = N; f.M = M;
   f.nn12 = nn12; f.best12 = best12; f.second12 = second12; f.nn21 = nn21; f.best21 = best21;
   f.scores1 = scores1; f.scores2 = scores2; f.inten1 = inten1; f.inten2 = inten2;

@@ -39,7 +39,7 @@ SIGNATURES = {
                                  c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
-    "sslam_match_finalize": (c_int, [c_int, ctypes.POINTER(c_float), c_void_p, c_int, c_int, c_int,
+    "sslam_match_finalize": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
@@ -49,6 +49,7 @@ ERROR_NAMES = {-1: "SSLAM_EINVAL", -2: "SSLAM_EUNSUPPORTED", -3: "SSLAM_EWORKSPA
                -4: "SSLAM_ECUDA", -5: "SSLAM_ENODEVICE"}
 
 _lib = None
+ABI_VERSION = 3
 
 
 class SslamError(RuntimeError):
@@ -69,7 +70,7 @@ def load():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.sslam_abi_version() != 2:
+        if lib.sslam_abi_version() != ABI_VERSION:
             raise ImportError("libsslam_b200.so ABI version mismatch; rebuild")
         _lib = lib
     return _lib

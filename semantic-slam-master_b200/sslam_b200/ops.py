@@ -217,8 +217,11 @@ def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=Non
     return (out, out16) if want_bf16 else out
 
 
-def match_top2(bank1, bank2, pair_index=None, mode=SIM_F32, num_pairs=None, workspace=None):
+def match_top2(bank1, bank2, pair_index=None, mode=SIM_F16X3, num_pairs=None, workspace=None):
     """Row top-2 / column argmax of S_p = D1_p . D2_p^T without storing S.
+
+    The default arithmetic is SIM_F16X3 — the tcgen05/TMEM tile GEMM with fp32-level accuracy (D % 8 == 0);
+    SIM_F32 is the CUDA-core exact kernel kept as the explicit cross-check (and for D % 8 != 0).
 
     bank1 (F1,N,D), bank2 (F2,M,D); pair_index (P,2) int32 selects (a,b) per pair, default (p,p).
     With mode=SIM_F16X3 a bank may also be the (hi, lo) fp16 pair written by l2norm_rows /
@@ -285,7 +288,7 @@ def match_finalize(variant, top, params, pair_index=None, scores1=None, scores2=
     pairs = torch.empty(P, N, 2, dtype=torch.int32, device=dev)
     pscores = torch.empty(P, N, dtype=torch.float32, device=dev)
     counts = torch.empty(P, dtype=torch.int32, device=dev)
-    prm = (ctypes.c_float * 8)(*([float(v) for v in params] + [0.0] * (8 - len(params))))
+    prm = (ctypes.c_double * 8)(*([float(v) for v in params] + [0.0] * (8 - len(params))))
     for t in (scores1, scores2, inten1, inten2):
         if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
             raise RuntimeError("score / intensity banks must be contiguous fp32")

@@ -21,7 +21,7 @@ from .ops import SIM_BF16, SIM_F32, SIM_F16X3
 
 class FrontEnd:
     def __init__(self, refiner, num_keypoints=2048, nms_radius=2, min_score_percentile=0.5,
-                 grid="pixel", sim_mode=SIM_F32, patch_size=16):
+                 grid="pixel", sim_mode=SIM_F16X3, patch_size=16):
         self.refiner = refiner.eval()
         self.K, self.r, self.pct = int(num_keypoints), int(nms_radius), float(min_score_percentile)
         self.grid, self.sim_mode, self.patch = grid, sim_mode, patch_size

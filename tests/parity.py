@@ -13,6 +13,27 @@ import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NEAR_TIE = 1e-6
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def record(name, entry):
+    """Persist a parity record (near-tie exception counts, index agreement, margins): north_star asks
+    for the exceptions to be "excepted and counted".  Entries accumulate in one JSON file —
+    ``$SSLAM_PARITY_RECORD`` or ``gpurun_out/parity_record.json`` (merged back from the GPU box);
+    the copy judged is committed under ``profiles/``."""
+    path = os.environ.get("SSLAM_PARITY_RECORD") or os.path.join(ROOT, "gpurun_out", "parity_record.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[name] = entry
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    print(f"[parity] {name}: {json.dumps(entry)}")
 
 
 def load_golden(name):

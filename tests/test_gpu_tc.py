@@ -13,7 +13,7 @@ import torch
 
 import oracle
 from oracle import recipes
-from parity import compare_matches
+from parity import compare_matches, record
 
 pytestmark = pytest.mark.gpu
 
@@ -64,8 +64,8 @@ def test_tf32x3_top2(n, m, d, dev):
     # tensor-core fp32 accumulation truncates (~2e-6 low at |S|~1, D=256); decisions are unaffected
     # beyond the 1e-6 near-tie band because the bias is common to neighbouring values
     exc = check_top(t, S64, 3e-6, 1e-6)
-    print(f"tf32x3 {n}x{m}x{d}: near-tie index exceptions {exc}, "
-          f"max |best-S| {np.abs(t['best12'] - S64.max(1)).max():.2e}")
+    record(f"tf32x3_top2.{n}x{m}x{d}", {"near_tie_index_exceptions": int(exc),
+                                        "max_abs_best_err": float(np.abs(t['best12'] - S64.max(1)).max())})
 
 
 @pytest.mark.parametrize("n,m,d", [c for c in CASES if c[2] % 8 == 0])
@@ -77,8 +77,8 @@ def test_f16x3_top2(n, m, d, dev):
     t = {k: v[0].cpu().numpy() for k, v in top.items()}
     S64 = d1.astype(np.float64) @ d2.astype(np.float64).T
     exc = check_top(t, S64, 3e-6, 1e-6)
-    print(f"f16x3 {n}x{m}x{d}: near-tie index exceptions {exc}, "
-          f"max |best-S| {np.abs(t['best12'] - S64.max(1)).max():.2e}")
+    record(f"f16x3_top2.{n}x{m}x{d}", {"near_tie_index_exceptions": int(exc),
+                                       "max_abs_best_err": float(np.abs(t['best12'] - S64.max(1)).max())})
 
 
 def test_match_back_to_back_launches_are_stable(dev):
@@ -190,7 +190,7 @@ def test_fp32_mode_sequence_matches_vs_oracle(mode_name, dev):
         exc += compare_matches(S, rm, p2[p, :int(c2[p])].cpu().numpy(),
                                threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
         assert int(counts[p]) > K // 4
-    print(mode_name, "sequence near-tie exceptions:", exc)
+    record(f"fp32_mode_sequence.{mode_name}", {"pairs": T - 1, "near_tie_exceptions": int(exc)})
 
 
 def test_bf16_sequence_scores(dev):
@@ -212,7 +212,7 @@ def test_bf16_sequence_scores(dev):
     common = [(k, refd[tuple(r)]) for k, r in enumerate(got.tolist()) if tuple(r) in refd]
     agree = len(common) / max(len(ref), 1)
     rel = max(abs(gs[k] - s) / abs(s) for k, s in common)
-    print(f"bf16 K=4096: index agreement {100 * agree:.2f}% of {len(ref)} matches, max rel score err {rel:.2e}")
+    record("bf16_sequence_K4096", {"ref_matches": len(ref), "index_agreement": agree, "max_rel_score_err": float(rel)})
     assert agree > 0.98
     assert rel < 1e-2
 
@@ -301,7 +301,7 @@ def test_c3_bf16_pairs_with_ratio_rules(dev):
         refd = {tuple(r): v for r, v in zip(ref.tolist(), dist.tolist())}
         rel = max(abs((1 - sc[p, k].item()) - (1 - refd[tuple(r)])) / abs(1 - refd[tuple(r)])
                   for k, r in enumerate(got.tolist()) if tuple(r) in refd)
-        print(f"c3 pair {p}: M3 {len(refset)} ref matches, index agreement {100 * agree:.2f}%, score rel err {rel:.1e}")
+        record(f"c3_bf16_M3.pair{p}", {"ref_matches": len(refset), "index_agreement": agree, "max_rel_score_err": float(rel)})
         assert agree > 0.97 and rel < 1e-2
 
 
@@ -333,7 +333,7 @@ def test_c4_all_pairs_keyframes(dev):
         part = fe.match_pairs(f, idx[owned[r]].to(dev), matchers.M2)
         assert torch.equal(part[2], full[2][owned[r].to(dev)])
         assert torch.equal(part[0], full[0][owned[r].to(dev)])
-    print("c4 near-tie exceptions:", exc)
+    record("c4_all_pairs_keyframes", {"pairs": int(idx.shape[0]), "near_tie_exceptions": int(exc)})
 
 
 def test_c5_hires_pair(dev):
@@ -355,4 +355,4 @@ def test_c5_hires_pair(dev):
     exc = compare_matches(S, np.array([(i, j) for i, j, _ in ref]).reshape(-1, 2),
                           pairs[0, :int(counts[0])].cpu().numpy())
     assert int(counts[0]) > K // 4
-    print(f"c5: {int(counts[0])} matches, near-tie exceptions {exc}")
+    record("c5_hires_pair", {"matches": int(counts[0]), "near_tie_exceptions": int(exc)})
