@@ -14,6 +14,8 @@
  *    (thread-local);
  *  - there is no CPU fallback: on a machine without an sm_100 device every compute entry point
  *    returns SSLAM_ENODEVICE.
+ *  - one process may drive several devices: device properties, kernel attributes and occupancy
+ *    answers are cached per device; calls act on the calling thread's current device.
  *  - tie rules: top-k order is (score descending, linear index y*W+x ascending); argmax returns
  *    the lowest maximal index (NumPy / torch-CPU behaviour).
  */
@@ -139,13 +141,13 @@ int sslam_l2norm_rows(const float* in, int rows, int D, float eps, float* out_f3
 
 /* ---------------------------------------------------------------------------------------------
  * DescriptorRefiner forward (models/descriptor_refiner.py:58-91, 108-126): Linear+ReLU, `blocks`
- * pre-LayerNorm residual blocks, Linear, L2 normalise — tcgen05 tf32x3 GEMMs (fp32-level accuracy)
+ * pre-LayerNorm residual blocks, Linear, L2 normalise — tcgen05 f16x3 GEMMs (fp32-level accuracy)
  * with fused bias / residual / ReLU epilogues.
  *   params : HOST array of 4 + 8*blocks DEVICE pointers (fp32), in state_dict order:
  *            input_proj.{weight [Hd,C], bias}; per block norm1.{weight,bias}, fc1.{weight [Hd,Hd],
  *            bias}, norm2.{weight,bias}, fc2.{weight,bias}; output_proj.{weight [D,Hd], bias}
  *   packed : device buffer of sslam_refiner_packed_bytes(), filled once per weight set by
- *            sslam_refiner_pack_weights() (tf32 hi/lo copies of the Linear weights)
+ *            sslam_refiner_pack_weights() (fp16 hi/lo pairs of the Linear weights, LayerNorms folded)
  *   x [rows,C] fp32 (or NULL with the pair x_hi/x_lo [rows,C] fp16 from sslam_gather_bilinear_f32)
  *   -> out_f32 [rows,D] fp32 and/or out_bf16 [rows,D] bf16 and/or the fp16 pair out_hi/out_lo
  *      [rows,D] (see sslam_l2norm_rows), unit L2 norm
@@ -197,6 +199,46 @@ int sslam_match_finalize(int variant, const double* params /* host, 8 doubles; r
                          const float* best21, const float* scores1, const float* scores2,
                          const float* inten1, const float* inten2, int32_t* pairs,
                          float* pair_scores, int32_t* counts, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Evaluation adaptors — nearest (warped) keypoint, ground-truth match lists and
+ * match scoring for P keypoint-set pairs at once.  Replaces the N x M distance matrices of
+ * DescriptorQualityTester.compute_ground_truth_matches / evaluate_matches
+ * (test/test_descriptor_quality.py:144-183, 185-231) and RepeatabilityTester.compute_repeatability
+ * (test/test_repeatability.py:79-128).
+ *   kpts1 [F1,N,2], kpts2 [F2,M,2] fp32 (x,y); pair p reads sets (a,b) = pair_index[p] (int32 [P,2]) or (p,p)
+ *   H     [P,9] double, row-major homographies frame1 -> frame2, or NULL
+ *   min_dist [P,N]: DOUBLE when H != NULL (the reference promotes to float64 when it warps), FLOAT when
+ *             H == NULL (test_repeatability.py:104-105 subtracts and norms the float32 arrays)
+ *   argmin   [P,N] int32, lowest index of the minimum
+ */
+int sslam_nn_points(const float* kpts1, int F1, const float* kpts2, int F2, const double* H,
+                    const int32_t* pair_index, int P, int N, int M, void* min_dist, int32_t* argmin,
+                    void* stream);
+
+/* rows with min_dist < threshold, ascending i, as (i, argmin[i]) (test_descriptor_quality.py:173-181);
+ * pairs [P,N,2] int32 (-1 padded) may be NULL when only counts [P] (the repeatable count,
+ * test_repeatability.py:116) are wanted. */
+int sslam_gt_matches(const void* min_dist, const int32_t* argmin, int is_double, double threshold, int P,
+                     int N, int32_t* pairs, int32_t* counts, void* stream);
+
+/* tp / fp / fn of predicted against ground-truth lists (test_descriptor_quality.py:202-215); both
+ * lists hold each first index at most once.  pred [P,pred_stride,2], gt [P,gt_stride,2] int32 with
+ * their counts [P]; scratch [P,N] int32; out [P,3] int32. */
+int sslam_eval_matches(const int32_t* pred, const int32_t* pred_counts, int pred_stride,
+                       const int32_t* gt, const int32_t* gt_counts, int gt_stride, int P, int N,
+                       int32_t* scratch, int32_t* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optional cell-softmax front stage of the decode (north_star "softmax/depth-to-space ... border
+ * mask"; OFF by default — the reference code has no such mode, keypoint_selector.py:61-62 is a
+ * sigmoid; the vocabulary is papers/pdfs/SuperPoint_DeTone.md:49-58):
+ *   logits [B, cell*cell+1, Hc, Wc] fp32 -> softmax over channels, last channel dropped,
+ *   depth-to-space to heat [B, Hc*cell, Wc*cell], pixels closer than `border` to an edge zeroed.
+ * cell in {2,4,8}.  The heatmap is then decoded by sslam_decode_topk_f32.
+ */
+int sslam_heatmap_from_cells_f32(const float* logits, int B, int Hc, int Wc, int cell, int border,
+                                 float* heat, void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,3 +33,4 @@ from .gather import (extract_at_keypoints, patch_to_pixel, pixel_to_patch,  # no
 from .refiner import RefinerWeights, refiner_forward  # noqa: F401
 from .match import (similarity_top2, match_m1, match_m2, match_m3, match_m4,  # noqa: F401
                     match_m5)
+from . import evaluation  # noqa: F401,E402

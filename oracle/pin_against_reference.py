@@ -54,7 +54,8 @@ def load_reference(ref_root):
     from visualize_matches_sequence import SequenceMatcher
     from train import SemanticSLAMTrainer
     from test_descriptor_quality import DescriptorQualityTester
-    return dict(KeypointSelector=KeypointSelector, DinoBackbone=DinoBackbone,
+    from test_repeatability import RepeatabilityTester
+    return dict(RepeatabilityTester=RepeatabilityTester, KeypointSelector=KeypointSelector, DinoBackbone=DinoBackbone,
                 DescriptorRefiner=DescriptorRefiner, MatchVisualizer=MatchVisualizer,
                 SequenceMatcher=SequenceMatcher, SemanticSLAMTrainer=SemanticSLAMTrainer,
                 DescriptorQualityTester=DescriptorQualityTester)
@@ -316,6 +317,63 @@ def gen_match(ref):
     print("match.npz:", len(meta), "cases")
 
 
+# --------------------------------------------------------------------------- evaluation adaptors
+def eval_case(n, m, seed, H_kind):
+    """Integer-valued pixel keypoints (as the decode emits) of two frames related by a homography."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    k1 = np.stack([rng.integers(0, 640, size=n), rng.integers(0, 480, size=n)], 1).astype(np.float32)
+    if H_kind == "shift":
+        H = np.array([[1.0, 0.0, 16.0], [0.0, 1.0, -3.0], [0.0, 0.0, 1.0]])
+    elif H_kind == "persp":
+        H = np.array([[1.02, 0.015, 5.5], [-0.01, 0.98, 2.25], [1e-5, -2e-5, 1.0]])
+    else:
+        H = np.eye(3)
+    homo = np.concatenate([k1.astype(np.float64), np.ones((n, 1))], 1)
+    w = (H @ homo.T).T
+    w = w[:, :2] / w[:, 2:3]
+    # frame-2 keypoints: a shuffled subset of the warped points rounded to pixels (+ jitter), plus fresh ones
+    keep = rng.permutation(n)[: min(n, m) * 2 // 3]
+    k2 = np.round(w[keep] + rng.integers(-2, 3, size=(keep.size, 2))).astype(np.float32)
+    extra = np.stack([rng.integers(0, 640, size=m - keep.size), rng.integers(0, 480, size=m - keep.size)], 1)
+    k2 = np.concatenate([k2, extra.astype(np.float32)], 0)[rng.permutation(m)]
+    return k1, np.ascontiguousarray(k2), H
+
+
+EVAL_CASES = {"small_shift": (200, 180, 71, "shift"), "persp": (500, 640, 72, "persp"),
+              "k2048": (2048, 2048, 73, "persp"), "ident": (64, 64, 74, "ident")}
+
+
+def gen_evaluation(ref):
+    DQ, RT = ref["DescriptorQualityTester"], ref["RepeatabilityTester"]
+    blob = {"versions": versions()}
+    meta = {}
+    for name, (n, m, seed, kind) in EVAL_CASES.items():
+        k1, k2, H = eval_case(n, m, seed, kind)
+        blob[name + ".k1"], blob[name + ".k2"], blob[name + ".H"] = k1, k2, H
+        for thr in (3.0, 1.0):
+            gt = DQ.compute_ground_truth_matches(None, k1, k2, H, thr)
+            blob[f"{name}.gt{thr:g}"] = gt.astype(np.int64).reshape(-1, 2)
+        gt = blob[name + ".gt3"]
+        # a "prediction": half of the gt pairs, plus wrong pairs on other rows
+        rng = np.random.Generator(np.random.PCG64(seed + 5))
+        pred = gt[::2].copy()
+        free = np.setdiff1d(np.arange(n), gt[:, 0])[:40]
+        wrong = np.stack([free, rng.integers(0, m, size=free.size)], 1)
+        pred = np.concatenate([pred, wrong], 0).astype(np.int64)
+        blob[name + ".pred"] = pred
+        ev = DQ.evaluate_matches(None, pred, gt, n, m)
+        blob[name + ".eval"] = np.array([ev["tp"], ev["fp"], ev["fn"]], dtype=np.int64)
+        blob[name + ".evalf"] = np.array([ev["precision"], ev["recall"], ev["f1"], ev["inlier_ratio"]])
+        for tag, HH in (("repH", H), ("rep0", None)):
+            r = RT.compute_repeatability(None, k1, k2, HH, 3.0)
+            blob[f"{name}.{tag}"] = np.array([r["repeatability"], float(r["repeatable_count"]),
+                                              float(r["mean_nn_distance"]), float(r["median_nn_distance"])])
+        meta[name] = dict(n=n, m=m, seed=seed, H=kind)
+    blob["meta"] = json.dumps(meta)
+    np.savez_compressed(os.path.join(GOLDEN, "evaluation.npz"), **blob)
+    print("evaluation.npz:", len(meta), "cases")
+
+
 # --------------------------------------------------------------------------- reference CPU timing
 def gen_timing(ref, frames=6):
     """Times the unmodified reference functions on c1/c2-shaped inputs in THIS container
@@ -371,7 +429,7 @@ def main():
     args = ap.parse_args()
     os.makedirs(GOLDEN, exist_ok=True)
     ref = load_reference(args.reference)
-    todo = args.only.split(",") if args.only else ["quantile", "decode", "gather", "refiner", "match"]
+    todo = args.only.split(",") if args.only else ["quantile", "decode", "gather", "refiner", "match", "evaluation"]
     if "quantile" in todo:
         gen_quantile()
     if "decode" in todo:
@@ -382,6 +440,8 @@ def main():
         gen_refiner(ref)
     if "match" in todo:
         gen_match(ref)
+    if "evaluation" in todo:
+        gen_evaluation(ref)
     if args.timing:
         gen_timing(ref)
 

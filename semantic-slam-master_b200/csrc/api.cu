@@ -66,18 +66,47 @@ static int query_device(int* sms) {
   return SSLAM_OK;
 }
 
-static std::once_flag g_once;
-static int g_dev_rc = SSLAM_ENODEVICE;
-static int g_sms = 0;
+// per-device cache (compute capability and SM count are properties of a device, and one process
+// may drive several): state 0 = not queried, 1 = usable, 2 = not usable
+constexpr int MAX_DEVICES = 64;
+static std::atomic<int> g_dev_state[MAX_DEVICES];
+static std::atomic<int> g_dev_sms[MAX_DEVICES];
+static std::atomic<int> g_nodevice{0};              // no device visible at all (cached)
 
 int check_device() {
-  std::call_once(g_once, [] { g_dev_rc = query_device(&g_sms); });
-  if (g_dev_rc != SSLAM_OK && g_err[0] == 0)
-    set_error("no usable sm_100 CUDA device; libsslam_b200 has no CPU fallback");
-  return g_dev_rc;
+  if (g_nodevice.load(std::memory_order_relaxed)) {
+    set_error("no CUDA device visible; libsslam_b200 has no CPU fallback");
+    return SSLAM_ENODEVICE;
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = -1; }
+  if (dev >= 0 && dev < MAX_DEVICES) {
+    const int st = g_dev_state[dev].load(std::memory_order_acquire);
+    if (st == 1) return SSLAM_OK;
+    if (st == 2) {
+      set_error("device %d is not an sm_100 device; libsslam_b200 has no CPU fallback", dev);
+      return SSLAM_ENODEVICE;
+    }
+  }
+  int sms = 0;
+  const int rc = query_device(&sms);
+  if (dev < 0) {
+    if (rc == SSLAM_ENODEVICE) g_nodevice.store(1);
+    return rc;
+  }
+  if (dev < MAX_DEVICES && (rc == SSLAM_OK || rc == SSLAM_ENODEVICE)) {
+    g_dev_sms[dev].store(sms);
+    g_dev_state[dev].store(rc == SSLAM_OK ? 1 : 2, std::memory_order_release);
+  }
+  return rc;
 }
 
-int num_sms() { return g_sms > 0 ? g_sms : 148; }
+int num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return 148;
+  const int s = g_dev_sms[dev].load();
+  return s > 0 ? s : 148;
+}
 
 }  // namespace sslam
 
@@ -99,7 +128,8 @@ extern "C" uint64_t sslam_launch_count(void) { return sslam::g_launches.load(); 
 
 static const char* const kKindNames[sslam::KK_COUNT] = {
     "decode_scan", "decode_topk", "decode_count", "decode_resolve", "nms", "gather", "l2norm",
-    "match_f32", "match_tc", "split_pair", "unpack_cols", "match_finalize", "gemm_f16x3", "layernorm"};
+    "match_f32", "match_tc", "split_pair", "unpack_cols", "match_finalize", "gemm_f16x3", "layernorm",
+    "eval_points", "cell_softmax", "conv_head"};
 
 extern "C" int sslam_profile_enable(int on) {
   std::lock_guard<std::mutex> lk(sslam::g_prof_mu);

@@ -17,8 +17,23 @@ typedef unsigned int u32;
 
 // ---------------------------------------------------------------------------- host side
 void set_error(const char* fmt, ...);
-int check_device();                    // cached; SSLAM_OK or error
-int num_sms();
+int check_device();                    // cached per device; SSLAM_OK or error
+int num_sms();                         // of the calling thread's current device
+// True exactly once per (call site, device): function attributes (dynamic shared memory size) and
+// occupancy answers are per device, so a process that drives several GPUs configures each of them.
+//   static DeviceOnce once;  if (once.first_use()) { cudaFuncSetAttribute(...); }
+struct DeviceOnce {
+  std::atomic<uint64_t> done[2] = {};
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    const uint64_t bit = 1ull << (dev & 63);
+    std::atomic<uint64_t>& w = done[(dev >> 6) & 1];
+    if (w.load(std::memory_order_acquire) & bit) return false;
+    w.fetch_or(bit, std::memory_order_acq_rel);
+    return true;
+  }
+};
 extern std::atomic<uint64_t> g_launches;
 
 #define SSLAM_CHECK_CUDA(expr)                                                        \
@@ -42,7 +57,8 @@ extern std::atomic<uint64_t> g_launches;
 // kernel kinds for the launch counter / optional per-kernel event timing (sslam_profile_*)
 enum KernelKind {
   KK_DECODE_SCAN = 0, KK_DECODE_TOPK, KK_DECODE_COUNT, KK_DECODE_RESOLVE, KK_NMS, KK_GATHER, KK_L2NORM,
-  KK_MATCH_F32, KK_MATCH_TC, KK_SPLIT, KK_UNPACK, KK_FINALIZE, KK_GEMM, KK_LAYERNORM, KK_COUNT
+  KK_MATCH_F32, KK_MATCH_TC, KK_SPLIT, KK_UNPACK, KK_FINALIZE, KK_GEMM, KK_LAYERNORM, KK_EVAL, KK_HEATMAP,
+  KK_CONV_HEAD, KK_COUNT
 };
 extern std::atomic<int> g_profile_on;
 void prof_mark(int kind, cudaStream_t stream, bool begin);

@@ -699,13 +699,12 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
 
   const int kpad = next_pow2(K);
   size_t sel_smem = (size_t)kpad * 8 + sizeof(SelectScratch);
-  static std::atomic<size_t> configured{0};
-  if (configured.load() < sel_smem) {
+  static DeviceOnce once;
+  if (once.first_use()) {
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_topk_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_resolve_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured.store(160 * 1024);
   }
   SSLAM_LAUNCH(KK_DECODE_TOPK, stream,
                decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));

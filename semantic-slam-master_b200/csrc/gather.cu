@@ -372,13 +372,12 @@ extern "C" int sslam_gather_bilinear_f32(const float* feat, const float* kpts, i
   const size_t band_smem = 3 * (size_t)w * C * 4 + (size_t)N * (sizeof(BandGeo) + 2) + 64;
   if (vec && ((size_t)w * C * 4) % 16 == 0 && N <= 65535 && band_smem <= 227 * 1024 - 256 &&
       (reinterpret_cast<uintptr_t>(kpts) & 7) == 0 && ((out != nullptr) != (out_hi != nullptr))) {
-    static std::atomic<bool> configured{false};
-    if (!configured.load()) {
+    static DeviceOnce once;
+    if (once.first_use()) {
       SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gather_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024 - 256));
       SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gather_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024 - 256));
-      configured.store(true);
     }
     // bands -1 .. h-1 in groups of consecutive bands; about eight CTAs per SM over the launch so
     // that the tail is short, at least three bands per group so that the shared row stays cheap

@@ -359,11 +359,10 @@ extern "C" int sslam_match_top2(const void* bank1, const void* bank1_lo, int F1,
     mp.nn12 = nn12; mp.best12 = best12; mp.second12 = second12; mp.colkeys = colkeys;
     const int dpad = (D + BK - 1) / BK * BK;
     size_t smem = ((size_t)dpad * LDS_ + 2 * BK * LDS_) * 4 + 8 * BN * sizeof(u64);
-    static std::atomic<bool> configured{false};
-    if (!configured.load()) {
+    static DeviceOnce once;
+    if (once.first_use()) {
       SSLAM_CHECK_CUDA(cudaFuncSetAttribute(match_f32_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured.store(true);
     }
     dim3 grid((N + BM - 1) / BM, P);
     SSLAM_LAUNCH(KK_MATCH_F32, stream,

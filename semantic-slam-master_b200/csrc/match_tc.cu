@@ -290,11 +290,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
 // (~42 B/cycle/SM measured), not the tensor pipe.  Here the strip is loaded once per work item and
 // stays in shared memory (per-k-block barriers, so the next item's strip streams in while the last
 // tile of the current item is still being multiplied); only B tiles stream, in 16 KB stages.
-// f16x3 issues two MMAs per k-step instead of three: B_hi and B_lo tiles are adjacent in the stage,
-// so  A_hi x [B_hi ; B_lo]  is ONE N=256 instruction writing hi.hi into TMEM columns [0,128) and
-// hi.lo into [128,256); A_lo x B_hi (N=128) then accumulates into [128,256).  Same tensor work, one
-// A_hi operand read less per step.  Eight epilogue warps (two per TMEM lane quarter, 64 columns each)
-// keep the epilogue under the MMA time of a tile.
+// f16x3 issues three M=256 (cta_group::2) MMAs per k-step — A_lo x B_hi and A_hi x B_lo into the
+// cross-term accumulator (TMEM columns [128,256)), A_hi x B_hi into the main one ([0,128)); each CTA
+// of the pair holds half of every B tile.  Eight epilogue warps (two per TMEM lane quarter, 64 columns
+// each) keep the epilogue under the MMA time of a tile.
 template <int MODE> struct RCfg;
 template <> struct RCfg<SSLAM_SIM_F16X3> {
   static constexpr int TERMS = 2, B_BK = 64, B_SWZ = 128, B_STAGES = 4, ACC_COLS = 2 * BN, TMEM_COLS = 512;
@@ -735,11 +734,10 @@ template <int MODE>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                      const CUtensorMap& b_lo, const TcParams& tp, cudaStream_t stream) {
   using L = SmemLayout<MODE>;
-  static std::atomic<bool> configured{false};
-  if (!configured.load()) {
+  static DeviceOnce once;
+  if (once.first_use()) {
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(match_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           L::TOTAL));
-    configured.store(true);
   }
   const int strips = (tp.N + BM - 1) / BM;
   SSLAM_LAUNCH(KK_MATCH_TC, stream,
@@ -751,11 +749,10 @@ template <int MODE>
 static int launch_res(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi,
                       const CUtensorMap& b_lo, const TcParams& tp, cudaStream_t stream) {
   using L = RSmem<MODE>;
-  static std::atomic<bool> configured{false};
-  if (!configured.load()) {
+  static DeviceOnce once;
+  if (once.first_use()) {
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(match_res_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           L::TOTAL));
-    configured.store(true);
   }
   const int items = ((((tp.N + BM - 1) / BM) + 1) / 2) * tp.P;      // (pair of sets, strip pair)
   const int pairs = items < num_sms() / 2 ? items : num_sms() / 2;

@@ -779,11 +779,10 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
     if ((rc = make_tensor_map_2d(&to_f32, out_f32, rows, N, 32, UNIT, 4, 0))) return rc;
     to_hi = to_f32; to_lo = to_f32;
   }
-  static std::atomic<bool> configured{false};
-  if (!configured.load()) {
+  static DeviceOnce once;
+  if (once.first_use()) {
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           SMEM_TOTAL));
-    configured.store(true);
   }
   GemmParams gp;
   gp.rows = rows; gp.N = N; gp.K = K; gp.bias = bias; gp.res_hi = residual.hi; gp.res_lo = residual.lo;
@@ -802,20 +801,23 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
 #define SSLAM_PAIR_LAUNCH(LN_, RES_, RELU_, F32_, ST_)                                                     \
   do {                                                                                                     \
     auto kfn = gemm_pair_kernel<LN_, RES_, RELU_, F32_, ST_>;                                              \
-    static std::atomic<int> max_clusters[5] = {};                 /* per cluster shape, 0 = not queried */  \
+    static std::atomic<int> max_clusters[64][5] = {};             /* per device and cluster shape, 0 = not queried */ \
+    int dev_ = 0;                                                                                          \
+    SSLAM_CHECK_CUDA(cudaGetDevice(&dev_));                                                                \
+    dev_ &= 63;                                                                                            \
     cudaLaunchConfig_t cfg = {};                                                                           \
     cudaLaunchAttribute attr[1];                                                                           \
     attr[0].id = cudaLaunchAttributeClusterDimension;                                                      \
     attr[0].val.clusterDim.x = 2 * ntile; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;      \
     cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = P_SMEM_TOTAL; cfg.stream = stream;            \
     cfg.attrs = attr; cfg.numAttrs = 1;                                                                    \
-    int mcl = max_clusters[ntile].load();                                                                  \
+    int mcl = max_clusters[dev_][ntile].load();                                                               \
     if (mcl == 0) {                                                                                        \
       SSLAM_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_TOTAL)); \
       cfg.gridDim = dim3(2 * ntile);                                                                       \
       SSLAM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&mcl, kfn, &cfg));                                   \
       SSLAM_REQUIRE(mcl >= 1, SSLAM_EUNSUPPORTED, "refiner: no cluster of %d CTAs fits on this device", 2 * ntile); \
-      max_clusters[ntile].store(mcl);                                                                      \
+      max_clusters[dev_][ntile].store(mcl);                                                                \
     }                                                                                                      \
     groups = mcl < nsp ? mcl : nsp;                               /* all clusters co-resident */            \
     cfg.gridDim = dim3(2u * ntile * groups);                                                               \

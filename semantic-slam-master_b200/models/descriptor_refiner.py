@@ -2,7 +2,7 @@
 
 Same surface and ``state_dict`` layout as the reference (models/descriptor_refiner.py:11-126
 there): ``input_proj``, ``residual_blocks.{i}.{norm1,fc1,norm2,fc2}``, ``output_proj``.  Under
-``torch.no_grad()`` on a CUDA device the whole forward — six Linear layers as tcgen05 tf32x3 GEMMs
+``torch.no_grad()`` on a CUDA device the whole forward — six Linear layers as tcgen05 f16x3 GEMMs (fp16 hi/lo pairs, three MMAs per product)
 with fused bias/ReLU/residual epilogues, LayerNorms, and the final ``F.normalize`` — is one call
 into ``sslam_refiner_forward_f32``.  When autograd is recording (training is
 out of scope) the PyTorch ops are used so gradients exist; ``mlp="torch"`` forces that path for

@@ -55,8 +55,16 @@ class DinoBackbone(nn.Module):
     def extract_at_keypoints(self, patch_features: torch.Tensor, keypoints: torch.Tensor) -> torch.Tensor:
         """Bilinear sampling of (B, H, W, C) features at (B, N, 2) PATCH coordinates -> (B, N, C),
         with grid_sample(align_corners=True, zero padding) arithmetic."""
-        if patch_features.requires_grad or keypoints.requires_grad:
-            raise RuntimeError("extract_at_keypoints kernel has no backward; call under torch.no_grad()")
+        if torch.is_grad_enabled() and (patch_features.requires_grad or keypoints.requires_grad):
+            # training (out of scope for the kernels, which have no backward) needs autograd: the
+            # reference's own ops (models/dino_backbone.py:131-150 there), as DescriptorRefiner does
+            H, W = patch_features.shape[1], patch_features.shape[2]
+            g = keypoints.clone()
+            g[..., 0] = 2.0 * g[..., 0] / (W - 1) - 1.0
+            g[..., 1] = 2.0 * g[..., 1] / (H - 1) - 1.0
+            out = torch.nn.functional.grid_sample(patch_features.permute(0, 3, 1, 2), g.unsqueeze(1), mode="bilinear",
+                                                  align_corners=True)
+            return out.squeeze(2).permute(0, 2, 1)
         return ops.gather_bilinear(patch_features, keypoints, pixel_coords=False)
 
     def extract_at_pixel_keypoints(self, patch_features, pixel_keypoints):

@@ -55,6 +55,18 @@ class KeypointSelector(nn.Module):
         return ops.decode_topk(saliency_map, num_keypoints, nms_radius=nms_radius,
                                min_score_percentile=min_score_percentile)
 
+    def select_keypoints_from_cells(self, cell_logits: torch.Tensor, num_keypoints: int = 500,
+                                    nms_radius: int = 2, min_score_percentile: float = 0.50,
+                                    cell: int = 8, border: int = 4):
+        """OPTIONAL decode mode, off by default (the reference code has no such mode; see
+        csrc/heatmap.cu): (B, cell*cell+1, Hc, Wc) cell logits -> channel softmax, dustbin dropped,
+        depth-to-space, border mask -> then the same NMS / percentile threshold / top-k as
+        ``select_keypoints`` on the (B, Hc*cell, Wc*cell) heatmap.  Returns (keypoints, scores, heatmap)."""
+        heat = ops.heatmap_from_cells(cell_logits, cell=cell, border=border)
+        kp, sc, _ = ops.decode_topk(heat, num_keypoints, nms_radius=nms_radius,
+                                    min_score_percentile=min_score_percentile)
+        return kp, sc, heat
+
     def _apply_nms(self, saliency: torch.Tensor, radius: int) -> torch.Tensor:
         """(B, H, W) -> (B, H, W): keep values equal to their (2r+1)^2 neighbourhood maximum."""
         if radius == 0:

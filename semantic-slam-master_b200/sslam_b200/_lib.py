@@ -43,6 +43,20 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
+    "sslam_nn_points": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                c_void_p, c_void_p, c_void_p]),
+    "sslam_gt_matches": (c_int, [c_void_p, c_void_p, c_int, ctypes.c_double, c_int, c_int, c_void_p, c_void_p,
+                                 c_void_p]),
+    "sslam_eval_matches": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_void_p, c_void_p, c_void_p]),
+    "sslam_heatmap_from_cells_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+
+# include/sslam_b200_debug.h (tools only)
+DEBUG_SIGNATURES = {
+    "sslam_debug_match_stalls": (None, [c_void_p]),
+    "sslam_debug_gemm_stalls": (None, [c_void_p]),
+    "sslam_debug_watchdog_gemm": (c_int, [c_void_p]),
 }
 
 ERROR_NAMES = {-1: "SSLAM_EINVAL", -2: "SSLAM_EUNSUPPORTED", -3: "SSLAM_EWORKSPACE",
@@ -67,7 +81,7 @@ def load():
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` or `make -C semantic-slam-master_b200/csrc`. There is no CPU fallback.")
         lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         if lib.sslam_abi_version() != ABI_VERSION:

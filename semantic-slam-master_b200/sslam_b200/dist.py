@@ -53,22 +53,27 @@ def all_gather_bank(bank, group=None):
     return out
 
 
+_gather_buffers = {}
+
+
 def gather_match_lists(pairs, pair_scores, counts, dst=0, group=None):
-    """Final collective: fixed-size padded records per pair — int32 pairs (P,N,2) with -1 sentinel,
-    fp32 scores (P,N), int32 counts (P) — gathered on `dst`.  Every rank must pass the same P, N.
+    """Final collective: ONE gather of fixed-size records — per pair an int32 row
+    [count | N (i, j) pairs, -1 padded | N fp32 score bits] (evaluation.pack_match_records) — into a
+    preallocated buffer on `dst`.  Every rank must pass the same P, N.
     Returns (pairs (world*P,N,2), scores (world*P,N), counts (world*P)) on dst, None elsewhere."""
+    from .evaluation import pack_match_records, unpack_match_records
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    outs = []
-    for t in (pairs, pair_scores, counts):
-        t = t.contiguous()
-        if rank == dst:
-            buf = [torch.empty_like(t) for _ in range(world)]
-            dist.gather(t, gather_list=buf, dst=dst, group=group)
-            outs.append(torch.cat(buf, dim=0))
-        else:
-            dist.gather(t, gather_list=None, dst=dst, group=group)
-    return tuple(outs) if rank == dst else None
+    rec = pack_match_records(pairs, pair_scores, counts)
+    if rank != dst:
+        dist.gather(rec, gather_list=None, dst=dst, group=group)
+        return None
+    key = (world, tuple(rec.shape), rec.device)
+    buf = _gather_buffers.get(key)
+    if buf is None:
+        buf = _gather_buffers[key] = torch.empty((world,) + tuple(rec.shape), dtype=rec.dtype, device=rec.device)
+    dist.gather(rec, gather_list=list(buf.unbind(0)), dst=dst, group=group)
+    return unpack_match_records(buf.reshape(world * rec.shape[0], rec.shape[1]))
 
 
 def compact_match_lists(pairs, pair_scores, counts):

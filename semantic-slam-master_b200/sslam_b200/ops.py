@@ -158,7 +158,7 @@ def _check_pair(pair, numel):
 
 
 class RefinerPlan:
-    """Device-side state for sslam_refiner_forward_f32: pointer table + packed tf32 hi/lo weights of
+    """Device-side state for sslam_refiner_forward_f32: pointer table + packed fp16 hi/lo weight pairs of
     one DescriptorRefiner-shaped parameter set (state_dict order)."""
 
     def __init__(self, tensors, C, Hd, D, blocks):
@@ -298,3 +298,75 @@ def match_finalize(variant, top, params, pair_index=None, scores1=None, scores2=
                                         _ptr(inten1), _ptr(inten2), _ptr(pairs), _ptr(pscores),
                                         _ptr(counts), _stream()))
     return pairs, pscores, counts
+
+
+# ---------------------------------------------------------------------------------- evaluation (N4)
+def nn_points(kpts1, kpts2, H=None, pair_index=None, num_pairs=None):
+    """Nearest keypoint of set 2 for every (optionally homography-warped) keypoint of set 1.
+
+    kpts1 (F1,N,2), kpts2 (F2,M,2) fp32; H (P,3,3) float64 or None; pair_index (P,2) int32 or None.
+    Returns (min_dist (P,N) float64 with H / float32 without, argmin (P,N) int32)."""
+    lib = _lib.load()
+    _need_cuda(kpts1, kpts2, H, pair_index)
+    k1, k2 = kpts1.contiguous(), kpts2.contiguous()
+    if k1.dtype != torch.float32 or k2.dtype != torch.float32:
+        raise RuntimeError("nn_points expects fp32 keypoints")
+    F1, N = k1.shape[0], k1.shape[1]
+    F2, M = k2.shape[0], k2.shape[1]
+    if pair_index is not None:
+        pair_index = pair_index.to(torch.int32).contiguous()
+        P = pair_index.shape[0]
+    else:
+        P = int(num_pairs) if num_pairs is not None else min(F1, F2)
+    if H is not None:
+        H = H.to(torch.float64).contiguous()
+        if H.numel() != P * 9:
+            raise RuntimeError("nn_points: H must hold one 3x3 matrix per pair")
+    md = torch.empty(P, N, dtype=torch.float64 if H is not None else torch.float32, device=k1.device)
+    am = torch.empty(P, N, dtype=torch.int32, device=k1.device)
+    _lib.check(lib.sslam_nn_points(_ptr(k1), F1, _ptr(k2), F2, _ptr(H), _ptr(pair_index), P, N, M, _ptr(md),
+                                   _ptr(am), _stream()))
+    return md, am
+
+
+def gt_matches(min_dist, argmin, threshold=3.0, want_pairs=True):
+    """Rows with min_dist < threshold as (i, argmin[i]), ascending i.
+    Returns pairs (P,N,2) int32 -1-padded (or None), counts (P,) int32."""
+    lib = _lib.load()
+    _need_cuda(min_dist, argmin)
+    P, N = min_dist.shape
+    md = min_dist.contiguous()
+    pairs = torch.empty(P, N, 2, dtype=torch.int32, device=md.device) if want_pairs else None
+    counts = torch.empty(P, dtype=torch.int32, device=md.device)
+    _lib.check(lib.sslam_gt_matches(_ptr(md), _ptr(argmin.contiguous()), int(md.dtype == torch.float64),
+                                    float(threshold), P, N, _ptr(pairs), _ptr(counts), _stream()))
+    return pairs, counts
+
+
+def eval_matches(pred_pairs, pred_counts, gt_pairs, gt_counts, num_kpts1):
+    """tp / fp / fn per pair (P,3) int32 of predicted against ground-truth padded pair lists."""
+    lib = _lib.load()
+    _need_cuda(pred_pairs, pred_counts, gt_pairs, gt_counts)
+    P = pred_pairs.shape[0]
+    pp, gp = pred_pairs.to(torch.int32).contiguous(), gt_pairs.to(torch.int32).contiguous()
+    scratch = torch.empty(P, int(num_kpts1), dtype=torch.int32, device=pp.device)
+    out = torch.empty(P, 3, dtype=torch.int32, device=pp.device)
+    _lib.check(lib.sslam_eval_matches(_ptr(pp), _ptr(pred_counts.to(torch.int32).contiguous()), pp.shape[1],
+                                      _ptr(gp), _ptr(gt_counts.to(torch.int32).contiguous()), gp.shape[1], P,
+                                      int(num_kpts1), _ptr(scratch), _ptr(out), _stream()))
+    return out
+
+
+# ---------------------------------------------------------------------------------- optional decode front stage (J1)
+def heatmap_from_cells(logits, cell=8, border=0):
+    """(B, cell*cell+1, Hc, Wc) fp32 cell logits -> (B, Hc*cell, Wc*cell) heatmap: channel softmax,
+    dustbin dropped, depth-to-space, border mask.  Off-by-default decode mode (no reference code)."""
+    lib = _lib.load()
+    _need_cuda(logits)
+    x = logits.contiguous()
+    if x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != cell * cell + 1:
+        raise RuntimeError("heatmap_from_cells expects fp32 (B, cell*cell+1, Hc, Wc) logits")
+    B, _, Hc, Wc = x.shape
+    heat = torch.empty(B, Hc * cell, Wc * cell, dtype=torch.float32, device=x.device)
+    _lib.check(lib.sslam_heatmap_from_cells_f32(_ptr(x), B, Hc, Wc, int(cell), int(border), _ptr(heat), _stream()))
+    return heat

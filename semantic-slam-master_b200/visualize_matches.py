@@ -49,13 +49,22 @@ class MatchVisualizer:
         self.refiner.eval()
 
     @torch.no_grad()
-    def features_from_patch_map(self, dino_features):
-        """The part of extract_features after the backbone: (1,h,w,C) -> dict of NumPy arrays."""
+    def _extract_device(self, dino_features):
+        """selector -> select_keypoints -> extract_at_keypoints -> refiner -> patch_to_pixel
+        (visualize_matches.py:79-95 there), everything still on the device.  The head runs once."""
         sal = self.selector(dino_features)
         kp, sc = self.selector.select_keypoints(sal, num_keypoints=self.config["model"]["num_keypoints"])
         desc = self.refiner(self.backbone.extract_at_keypoints(dino_features, kp))
-        return {"keypoints_pixel": self.backbone.patch_to_pixel(kp)[0].cpu().numpy(),
-                "scores": sc[0].cpu().numpy(), "descriptors": desc[0].cpu().numpy()}
+        return {"saliency": sal, "keypoints_patch": kp, "keypoints_pixel": self.backbone.patch_to_pixel(kp),
+                "scores": sc, "descriptors": desc}
+
+    @torch.no_grad()
+    def features_from_patch_map(self, dino_features):
+        """The part of extract_features after the backbone: (1,h,w,C) -> dict of NumPy arrays
+        (keypoints_pixel (K,2), scores (K,), descriptors (K,D); visualize_matches.py:97-99 there)."""
+        f = self._extract_device(dino_features)
+        return {"keypoints_pixel": f["keypoints_pixel"][0].cpu().numpy(),
+                "scores": f["scores"][0].cpu().numpy(), "descriptors": f["descriptors"][0].cpu().numpy()}
 
     @torch.no_grad()
     def extract_features(self, image_path: str):

@@ -21,8 +21,11 @@ def lib():
     return _lib
 
 
-def declared_symbols():
-    src = open(HEADER).read()
+DEBUG_HEADER = os.path.join(ROOT, "include", "sslam_b200_debug.h")
+
+
+def declared_symbols(header=HEADER):
+    src = open(header).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(sslam_[a-z0-9_]+)\s*\(", src)))
 
@@ -34,6 +37,15 @@ def test_header_symbols_exported(lib):
     for n in names:
         assert hasattr(handle, n), f"{n} declared in the header but not exported"
     assert set(names) == set(lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    dbg = declared_symbols(DEBUG_HEADER)
+    assert set(dbg) == set(lib.DEBUG_SIGNATURES)
+    for n in dbg:
+        assert hasattr(handle, n), f"{n} declared in the debug header but not exported"
+    # nothing is exported that no header declares
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and l.split()[-1].startswith("sslam_")}
+    assert exported == set(names) | set(dbg), exported ^ (set(names) | set(dbg))
 
 
 def test_abi_version_and_workspace_queries(lib):
