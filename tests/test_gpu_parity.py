@@ -203,7 +203,9 @@ def test_matchers_golden(name, dev):
     assert (np.diff(gp[:, 0]) > 0).all()                                  # ascending i
     exc += compare_matches(S, MAT[name + ".m1"], gp)
     if gp.shape == MAT[name + ".m1"].shape and np.array_equal(gp, MAT[name + ".m1"]):
-        assert np.allclose([s for _, _, s in got], MAT[name + ".m1s"], rtol=1e-6, atol=1e-6)
+        # default arithmetic = f16x3 on tcgen05: similarities within 3e-6 abs of fp64 (the tensor core
+        # truncates when it accumulates in fp32; tests/test_gpu_tc.py::test_f16x3_top2)
+        assert np.allclose([s for _, _, s in got], MAT[name + ".m1s"], rtol=0, atol=3e-6)
     second = lambda i: np.partition(S[i], -2)[-2] if S.shape[1] > 1 else -1.0  # noqa: E731
     got = matchers.find_matches(d1, d2, 1.02)
     exc += compare_matches(S, MAT[name + ".m1b"], np.array([(i, j) for i, j, _ in got]).reshape(-1, 2),
@@ -213,7 +215,7 @@ def test_matchers_golden(name, dev):
     assert mm.dtype == np.int64 and qq.dtype == np.float32 and mm.ndim == 2 and mm.shape[1] == 2
     exc += compare_matches(S, MAT[name + ".m2"], mm, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
     if np.array_equal(mm, MAT[name + ".m2"]):
-        assert np.allclose(qq, MAT[name + ".m2q"], rtol=1e-6, atol=1e-6)
+        assert np.allclose(qq, MAT[name + ".m2q"], rtol=0, atol=3e-6)
     mi, _ = matchers.match_with_quality(d1, d2, s1, s2, intensity1=i1, intensity2=i2,
                                         min_intensity=0.15, min_saliency=0.5)
     exc += compare_matches(S, MAT[name + ".m2i"], mi, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
@@ -225,7 +227,7 @@ def test_matchers_golden(name, dev):
         ratio_margin = lambda thr: (lambda i, j: abs(second(i) / (S[i, j] + 1e-8) - thr))  # noqa: E731
         exc += compare_matches(S, MAT[name + ".m3"], m3, threshold_margin=ratio_margin(0.9))
         if np.array_equal(m3, MAT[name + ".m3"]):
-            assert np.allclose(dist, MAT[name + ".m3d"], rtol=1e-5, atol=1e-6)
+            assert np.allclose(dist, MAT[name + ".m3d"], rtol=0, atol=3e-6)
         m3b, _ = matchers.find_mutual_nearest_neighbors(d1, d2, 0.98)
         exc += compare_matches(S, MAT[name + ".m3b"], m3b, threshold_margin=ratio_margin(0.98))
     if m["n"] == m["m"]:
@@ -319,7 +321,7 @@ def test_sequence_pipeline_vs_oracle(dev):
         gm = p2[p, :int(c2[p])].cpu().numpy()
         total_exc += compare_matches(S, rm, gm, threshold_margin=lambda i, j: abs(S[i, j] - 0.7))
         if np.array_equal(rm, gm):
-            assert np.allclose(q2[p, :int(c2[p])].cpu().numpy(), rq, rtol=1e-5, atol=1e-6)
+            assert np.allclose(q2[p, :int(c2[p])].cpu().numpy(), rq, rtol=0, atol=3e-6)
         assert int(counts[p]) > K // 4, "overlapping frames should match plentifully"
     record("sequence_pipeline_vs_oracle", {"pairs": T - 1, "near_tie_exceptions": int(total_exc)})
 
