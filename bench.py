@@ -1,26 +1,34 @@
 #!/usr/bin/env python
-"""bench.py — frame-pairs/s for extract+match @ 640x480, 2048 keypoints (BASELINE.json metric).
+"""bench.py — frame-pairs/s for extract+match (BASELINE.json metric), on 1..8 B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's CUDA path
-    python bench.py --impl reference [...]                       # CPU path (oracle port), host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path, workload c2
+    python bench.py --workload c3|c4|c5 [...]                       # the other BASELINE.json configs
+    python bench.py --scaling strong [...]                          # c2/c5: ONE sequence split over the ranks
+    python bench.py --impl reference [...]                          # the reference's CPU path, host cores
 
-Workload (BASELINE.json configs[1], "c2"): a TUM-RGB-D-shaped synthetic sequence of 600 frames,
-640x480 saliency maps + 30x40x384 NHWC feature maps already past the backbone, K = 2048 keypoints,
-D = 256, consecutive-pair matching with matcher M1 (ratio 0.8), fp32 mode (descriptors fp32; the
-similarity and the refiner GEMMs run as 3-term fp16 hi/lo splits on tcgen05, error < 3e-6 —
-`--mode tf32x3` is the TF32 variant, `--mode f32` the CUDA-core exact kernel, `--mode bf16` the bf16
-similarity of config c3).  One *step* is one
-pass over the whole sequence: every frame is extracted once (decode -> sample -> refiner MLP ->
-L2 norm) and each of the 599 consecutive pairs is matched.  With N GPUs every rank processes its
-own 600-frame sequence (weak scaling) and the match lists are gathered on rank 0 over NCCL.
+Workloads (BASELINE.json configs[1..4], made concrete in SURVEY.md §8(d)); inputs are the tensors the
+path sees after the backbone: saliency maps (T,H,W,1) fp32 and NHWC feature maps (T,H/16,W/16,384) fp32.
+  c2  TUM-RGB-D-shaped sequence, 600 frames 640x480, K=2048, D=256, consecutive pairs, M1 (ratio 0.8),
+      fp32 mode (f16x3 on tcgen05: fp32 in/out, 3-term fp16 hi/lo split).          [default, the metric]
+  c3  64 independent pairs (frames 2p, 2p+1 of sequence p), K=4096, bf16 similarity, M1 0.8 (+ M3 0.9).
+  c4  256 keyframes x K=2048, all 32 640 unordered pairs, M2; sharded by keyframe, descriptor banks
+      all-gathered over NCCL, pair tiles dealt block-cyclically, lists gathered on rank 0.
+  c5  1280x960 frames, K=8192, sequence of 600 frames, consecutive pairs, M1, fp32 mode.
+One *step* is one pass over the workload: every frame is extracted once (decode -> sample -> refiner MLP
+-> L2 norm) and every pair is matched.  --scaling weak (default): every rank runs its own sequence /
+pair set; strong: the one sequence of c2/c5 is split with shard_frames (one halo frame per rank), c3
+pairs are striped; c4 is always one keyframe set split over the ranks.
 
-`value`  : pairs / s with inputs resident in HBM, timed with CUDA events, max over ranks.
-`e2e`    : the same step through FrontEnd.run_sequence_host — inputs start in pinned HOST memory,
-           are streamed over PCIe inside the timed region, match lists are copied back.
-`roofline`: the dominant kernel of the step (by summed device time; today the tf32x3 GEMM of the
-           refiner MLP): algorithmic flops / CUDA-event duration, against the measured bf16 tensor
-           peak.  `kernels` lists every kernel kind the same way (HBM-bound ones against the copy peak).
-`cpu_baseline`: the oracle port of the same pipeline on the host cores, on a bounded sample.
+`value`   : pairs/s with inputs resident in HBM, CUDA events, max over ranks (CUDA-graph replay per step).
+`e2e`     : the same step from pinned HOST buffers through the public pipeline entry points, H2D and D2H
+            copies inside the timed region; `h2d_ceiling_gbs` is a bare pinned-copy probe of the same
+            buffers (no kernels) run right before it on every rank at once.
+`roofline`: the dominant kernel of the step: algorithmic flops or bytes / summed CUDA-event durations.
+`parity`  : the oracle's match lists for the same inputs (all pairs of c2 at N=1, a bounded sample
+            elsewhere) compared with the GPU's.
+`cpu_baseline` / --impl reference: the reference's own functions (from baseline/_ref, kind "reference")
+            or, when that tree is absent, the oracle port (kind "port"), in a process pool on all host cores.
+`gpu_eager_baseline`: the same pipeline in stock PyTorch ops on the same B200 (bounded sample).
 """
 
 import argparse
@@ -37,12 +45,6 @@ for p in (ROOT, PKG):
         sys.path.insert(0, p)
 
 _REAL_STDOUT = None
-# dram__bytes_read.sum + dram__bytes_write.sum of the refiner GEMM, per activation row, averaged over the
-# six launches of one refiner call in the committed `ncu --set full` capture
-# (profiles/r1b_all_kernels_full.txt, 614 400 rows: 1.86 / 1.88 / 2.84 / 1.87 / 2.83 / 1.54 GB); the
-# algorithmic figure for the same launches is 3 072 B per row (pair in + pair out) and 4 608 B with
-# the residual.
-NCU_GEMM_DRAM_BYTES_PER_ROW = 3475.0
 
 
 def emit(line):
@@ -53,7 +55,23 @@ def emit(line):
 
 METRIC = "frame-pairs/sec extract+match @640x480, 2048 kpts"
 UNIT = "frame-pairs/s"
-H, W, C, D = 480, 640, 384, 256
+C, HID, D = 384, 384, 256
+
+# name -> (H, W, K, frames, similarity mode, matcher, description)
+WORKLOADS = {
+    "c2": dict(H=480, W=640, K=2048, frames=600, mode="f16x3", kind="sequence",
+               text="c2: TUM RGB-D-shaped synthetic sequence, {frames} frames 640x480, consecutive-pair matching "
+                    "(M1 ratio 0.8), {K} kpts x 256-D, refiner MLP 384-384-384-256, fp32 mode"),
+    "c3": dict(H=480, W=640, K=4096, frames=128, mode="bf16", kind="pairs",
+               text="c3: {pairs} independent synthetic frame pairs 640x480, {K} kpts x 256-D, bf16 similarity, "
+                    "ratio test 0.8 (M1)"),
+    "c4": dict(H=480, W=640, K=2048, frames=256, mode="f16x3", kind="allpairs",
+               text="c4: loop-closure style all-pairs matching, {frames} keyframes x {K} kpts x 256-D ({pairs} pairs, "
+                    "M2), keyframes sharded, NCCL all-gather of descriptor banks + gather of match lists"),
+    "c5": dict(H=960, W=1280, K=8192, frames=600, mode="f16x3", kind="sequence",
+               text="c5: high-res 1280x960 synthetic sequence, {frames} frames, consecutive-pair matching (M1 ratio 0.8), "
+                    "{K} kpts x 256-D, fp32 mode"),
+}
 
 
 def parse():
@@ -62,21 +80,46 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=600)
-    ap.add_argument("--kpts", type=int, default=2048)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=0, help="override the workload's frame / keyframe count")
+    ap.add_argument("--kpts", type=int, default=0, help="override the workload's keypoints per frame")
     ap.add_argument("--mode", default="auto", choices=["auto", "f32", "tf32x3", "f16x3", "bf16"])
-    ap.add_argument("--chunk", type=int, default=300, help="frames per extraction launch group (device-resident arm)")
+    ap.add_argument("--chunk", type=int, default=0, help="frames per extraction launch group (0 = workload default)")
     ap.add_argument("--e2e-chunk", type=int, default=50, help="frames per host->device staging buffer (e2e arm)")
-    ap.add_argument("--cpu-sample-frames", type=int, default=601)
+    ap.add_argument("--cpu-sample-frames", type=int, default=0, help="frames per CPU-arm step (0 = sized to a time budget)")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="time budget of the whole --impl reference run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    return ap.parse_args()
+    a = ap.parse_args()
+    w = WORKLOADS[a.workload]
+    a.H, a.W, a.kind = w["H"], w["W"], w["kind"]
+    a.frames = a.frames or w["frames"]
+    a.kpts = a.kpts or w["K"]
+    a.mode_name = w["mode"] if a.mode == "auto" else a.mode
+    if a.mode == "auto" and os.environ.get("SSLAM_BENCH_MODE"):
+        a.mode_name = os.environ["SSLAM_BENCH_MODE"]
+    if not a.chunk:
+        a.chunk = 300 if a.workload != "c5" else 75          # ~10 GB of intermediates per launch group
+    return a
 
 
-def workload_name(a):
-    return (f"c2: TUM RGB-D-shaped synthetic sequence, {a.frames} frames {W}x{H}, consecutive-pair "
-            f"matching (M1 ratio 0.8), {a.kpts} kpts x {D}-D, refiner MLP 384-384-384-{D}")
+def total_pairs(a):
+    if a.kind == "sequence":
+        return a.frames - 1
+    if a.kind == "pairs":
+        return a.frames // 2
+    return a.frames * (a.frames - 1) // 2
+
+
+def workload_config(a):
+    """The `config` object — identical for the b200 and the reference arm (same workload, same keys)."""
+    pairs = total_pairs(a)
+    return {"workload": WORKLOADS[a.workload]["text"].format(frames=a.frames, K=a.kpts, pairs=pairs),
+            "name": a.workload, "frames": a.frames, "kpts": a.kpts, "pairs": pairs,
+            "height": a.H, "width": a.W, "descriptor_dim": D, "scaling": a.scaling, "n_gpus": a.gpus}
 
 
 def measured_peaks():
@@ -86,6 +129,19 @@ def measured_peaks():
             return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, \
         "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel, rows):
+    """dram bytes per launch of `kernel` from the newest committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py), scaled to this run's rows per
+    launch; None when no capture of this kernel is on file."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        with open(path) as f:
+            rec = json.load(f).get(kernel)
+        return rec["dram_bytes_per_row"] * rows if rec else None
+    except Exception:
+        return None
 
 
 # --------------------------------------------------------------------------------------- clocks
@@ -160,54 +216,191 @@ def physical_gpu_index(local):
     return local
 
 
-# --------------------------------------------------------------------------------------- CPU arm
-def cpu_pipeline_rate(a, frames, workers):
-    """Oracle port of the same pipeline on `frames` frames -> (pairs/s, seconds, pairs)."""
+# --------------------------------------------------------------------------------------- inputs
+def frame_plan(a, rank, world):
+    """Which frames this rank extracts and which pairs it matches.
+    Returns dict(seq, frames=[(seq_id, frame t)], pair_index (local frame indices) or None = consecutive,
+    npairs_local, npairs_global)."""
+    from sslam_b200 import dist as sdist
+    T = a.frames
+    if a.kind == "sequence":
+        if a.scaling == "strong" and world > 1:
+            s, e, n = sdist.shard_frames(T, world, rank)
+            return dict(frames=[(0, t) for t in range(s, e)], pair_index=None, npairs_local=n, npairs_global=T - 1,
+                        pad_pairs=-(-(T - 1) // world))
+        return dict(frames=[(rank, t) for t in range(T)], pair_index=None, npairs_local=T - 1,
+                    npairs_global=(T - 1) * world, pad_pairs=T - 1)
+    if a.kind == "pairs":
+        P = T // 2
+        mine = list(range(rank, P, world)) if (a.scaling == "strong" and world > 1) else list(range(P))
+        seq_off = 0 if (a.scaling == "strong" or world == 1) else rank * P
+        frames, idx = [], []
+        for k, p in enumerate(mine):                       # frames (2p, 2p+1) of sequence p (SURVEY §8(d))
+            frames += [(seq_off + p, 2 * p), (seq_off + p, 2 * p + 1)]
+            idx.append((2 * k, 2 * k + 1))
+        glob = P if (a.scaling == "strong" or world == 1) else P * world
+        return dict(frames=frames, pair_index=idx, npairs_local=len(mine), npairs_global=glob,
+                    pad_pairs=-(-P // world) if a.scaling == "strong" else P)
+    # all pairs: keyframes = frames 0, 8, 16, ... of sequence 0, contiguous blocks per rank
+    per = T // world
+    return dict(frames=[(0, 8 * k) for k in range(rank * per, (rank + 1) * per)], pair_index="allpairs",
+                npairs_local=None, npairs_global=T * (T - 1) // 2, pad_pairs=None)
+
+
+def make_inputs(a, plan, pinned=True):
+    """Seeded synthetic frames on the HOST (torch CPU generators: identical to what the oracle / the
+    reference arm generates), in pinned buffers that also serve the e2e arm."""
     import torch
-    import oracle
-    from oracle import pipeline as opipe
-    from models.descriptor_refiner import DescriptorRefiner
     from sslam_b200 import synth
+    n = len(plan["frames"])
+    sal = torch.empty((n, a.H, a.W, 1), dtype=torch.float32, pin_memory=pinned)
+    feat = torch.empty((n, a.H // 16, a.W // 16, C), dtype=torch.float32, pin_memory=pinned)
+    canvases = {}
+    for i, (seq, t) in enumerate(plan["frames"]):
+        cv = canvases.get(seq)
+        if cv is None:
+            if len(canvases) > 2:
+                canvases.clear()
+            cv = canvases[seq] = synth.WorldCanvas(seq, a.H, a.W, C, "cpu")
+        lg, ft = cv.frame(t)
+        sal[i, :, :, 0].copy_(torch.sigmoid(lg))
+        feat[i].copy_(ft)
+    return sal, feat
+
+
+def refiner_module(dev=None):
+    import torch
+    from models.descriptor_refiner import DescriptorRefiner
     torch.manual_seed(0)
-    weights = oracle.RefinerWeights.from_state_dict(DescriptorRefiner(C, 384, D, 4).state_dict())
-    sal, feat = synth.make_sequence(frames, seq_id=0, height=H, width=W)
-    counts, sec = opipe.run_sequence(sal.numpy()[..., 0], feat.numpy(), weights, a.kpts, 1, workers)
-    return (frames - 1) / sec, sec, frames - 1
+    m = DescriptorRefiner(C, HID, D, 4)
+    return m.to(dev) if dev is not None else m
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_arm_kind():
+    from oracle import ref_pipeline
+    return "reference" if ref_pipeline.available() else "port"
+
+
+def cpu_pipeline(a, frames, workers):
+    """The CPU arm on the first `frames` frames of the c2-style sequence 0 (or pairs of c3 / keyframes):
+    returns (pairs/s, seconds, [(count, crc32)] per consecutive pair, kind)."""
+    import numpy as np
+    import torch
+    from oracle import pipeline as opipe, ref_pipeline
+    import oracle
+    plan = dict(frames=[(0, t) for t in range(frames)])
+    sal, feat = make_inputs(a, plan, pinned=False)
+    refiner = refiner_module()
+    if ref_pipeline.available():
+        sd = {k: v.detach().numpy() for k, v in refiner.state_dict().items()}
+        rec, sec = ref_pipeline.run_sequence(sal.numpy()[..., 0], feat.numpy(), sd, (C, HID, D, 4), a.kpts, workers)
+        kind = "reference"
+    else:
+        weights = oracle.RefinerWeights.from_state_dict(refiner.state_dict())
+        rec, sec = opipe.run_sequence(sal.numpy()[..., 0], feat.numpy(), weights, a.kpts, 1, workers)
+        kind = "port"
+    del np, torch
+    return (frames - 1) / sec, sec, rec, kind
+
+
+def cpu_sample_text(kind, frames, workers, sec=None):
+    what = ("the reference's own select_keypoints / pixel_to_patch / extract_at_keypoints / DescriptorRefiner / "
+            "find_matches (baseline/_ref)" if kind == "reference" else "oracle port (NumPy)")
+    t = f"{frames} frames / {frames - 1} consecutive pairs of sequence 0 of the workload per step, {what}, " \
+        f"{workers}-process pool over frames then pairs"
+    return t + (f", {sec:.1f} s" if sec is not None else "")
 
 
 def run_reference(a):
-    """--impl reference: the reference is pure Python and cannot travel to the GPU box, so its CPU
-    implementation is represented by the oracle port (oracle/pipeline.py) on every host core."""
+    """--impl reference: the reference's CPU implementation of the path on every host core."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import pipeline as opipe
     cores = opipe.host_cores()
-    frames = max(3, a.cpu_sample_frames)
-    vals = []
+    frames = a.cpu_sample_frames
+    if frames <= 0:
+        # size the per-step sample so that the whole run (warm-ups + steps) fits the time budget
+        probe = 33 if a.kpts <= 4096 and a.H <= 480 else 9
+        _, sec, _, _ = cpu_pipeline(a, probe, cores)
+        per_frame = sec / probe
+        frames = int(a.cpu_budget_s / max(1, a.warmup + a.steps) / per_frame)
+        frames = max(17, min(frames, a.frames + 1))
+    vals, kind = [], None
     for i in range(a.warmup + a.steps):
-        v, sec, pairs = cpu_pipeline_rate(a, frames, cores)
+        v, sec, _, kind = cpu_pipeline(a, frames, cores)
         if i >= a.warmup:
             vals.append((v, sec))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(s for _, s in vals) / len(vals)
-    sample = f"{frames} frames / {frames - 1} pairs of the c2 workload per step, process pool over frames then pairs"
+    sample = cpu_sample_text(kind, frames, cores)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(a), "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "scaling": a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
 
+# --------------------------------------------------------------------------------------- stock-torch GPU baseline
+def gpu_eager_baseline(a, sal, feat, refiner, frames=16):
+    """The same pipeline in stock PyTorch ops on the same GPU (quantile / max_pool2d / topk /
+    grid_sample / linear + layer_norm (cuBLAS fp32) / normalize / mm / argmax), main decode branch,
+    consecutive pairs of the first `frames` frames; CUDA events.  Returns pairs/s."""
+    import torch
+    import torch.nn.functional as F
+    K = a.kpts
+    T = min(frames, sal.shape[0])
+    if T < 2:
+        return None
+
+    def extract(s, f):
+        s2 = s[:, :, 0]
+        thr = max(torch.quantile(s2.flatten(), 0.5).item(), 0.1)
+        pooled = F.max_pool2d(s2[None, None], 5, 1, 2)[0, 0]
+        nms = s2 * (s2 == pooled).float()
+        cand = torch.where(nms > thr, nms, torch.zeros_like(nms)).flatten()
+        sc, idx = torch.topk(cand, K)
+        xy = torch.stack([(idx % a.W).float(), (idx // a.W).float()], -1)
+        pc = (xy - 8.0) / 16.0
+        h, w = f.shape[0], f.shape[1]
+        g = torch.stack([2 * pc[:, 0] / (w - 1) - 1, 2 * pc[:, 1] / (h - 1) - 1], -1)[None, None]
+        samp = F.grid_sample(f.permute(2, 0, 1)[None], g, mode="bilinear", align_corners=True)[0, :, 0].t()
+        return F.normalize(refiner.forward_unnormalized(samp[None]), p=2, dim=-1), sc
+
+    def match(d1, d2):
+        S = d1 @ d2.t()
+        best, nn12 = S.max(1)
+        nn21 = S.argmax(0)
+        second = S.scatter(1, nn12[:, None], -1.0).max(1).values
+        ok = (nn21[nn12] == torch.arange(S.shape[0], device=S.device)) & (best > second * 0.8)
+        return torch.nonzero(ok).squeeze(1), nn12
+
+    with torch.no_grad():
+        for rep in range(2):                                   # first pass = warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            prev = None
+            for t in range(T):
+                d, _ = extract(sal[t], feat[t])
+                if prev is not None:
+                    match(prev, d)
+                prev = d
+            e1.record()
+            torch.cuda.synchronize()
+    return (T - 1) / (e0.elapsed_time(e1) * 1e-3)
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def run_b200(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from models.descriptor_refiner import DescriptorRefiner
     from sslam_b200 import dist as sdist
-    from sslam_b200 import matchers, ops, synth
+    from sslam_b200 import matchers, ops
     from sslam_b200.pipeline import FrontEnd
 
     rank = int(os.environ.get("RANK", "0"))
@@ -217,35 +410,77 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode_name = a.mode
-    if mode_name == "auto":
-        # "fp32 mode" of BASELINE config c2: fp32 in/out, 3-term fp16 hi/lo split on the tensor cores
-        mode_name = os.environ.get("SSLAM_BENCH_MODE", "f16x3")
-    mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16, "f16x3": ops.SIM_F16X3}[mode_name]
+    mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16, "f16x3": ops.SIM_F16X3}[a.mode_name]
+    variant = matchers.M2 if a.kind == "allpairs" else matchers.M1
+    mkw = {} if a.kind == "allpairs" else {"ratio_thresh": 0.8}
 
-    torch.manual_seed(0)
-    refiner = DescriptorRefiner(C, 384, D, 4).to(dev)
+    refiner = refiner_module(dev)
     fe = FrontEnd(refiner, num_keypoints=a.kpts, grid="pixel", sim_mode=mode)
-    T = a.frames
-    # per-rank sequence, generated on the device (seeded), sigmoid computed once and shared
-    sal, feat = synth.make_sequence(T, seq_id=rank, height=H, width=W, device=dev)
+    plan = frame_plan(a, rank, world)
+    sal_h, feat_h = make_inputs(a, plan)
+    sal, feat = sal_h.to(dev), feat_h.to(dev)
+    Tl = sal.shape[0]
     in_bytes = sal.numel() * 4 + feat.numel() * 4
+    K = a.kpts
+
+    # ---- the device-resident step
+    coll_ms = {"all_gather": [], "gather_lists": []}
+    if a.kind == "sequence":
+        run = lambda timers=None: fe.run_sequence(sal, feat, variant, chunk=a.chunk, timers=timers, **mkw)  # noqa: E731
+        pidx_local = None
+    elif a.kind == "pairs":
+        pidx_local = torch.tensor(plan["pair_index"], dtype=torch.int32, device=dev).reshape(-1, 2)
+        run = lambda timers=None: fe.run_pairs(sal, feat, pidx_local, variant, chunk=a.chunk, timers=timers, **mkw)  # noqa: E731
+    else:
+        all_idx = sdist.all_pairs_index(a.frames)
+        mine = sdist.deal_pairs_block_cyclic(all_idx, world, rank, block=16)
+        pidx_local = all_idx[mine].to(dev)
+        pad = -(-all_idx.shape[0] // world) + 16 * 16 * 2        # dealt tiles differ by up to two tiles
+
+        def run(timers=None):
+            f = fe.extract(sal, feat, timers=timers)
+            hi, lo, sc = f["descriptors_hi"], f["descriptors_lo"], f["scores"]
+            if world > 1:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+                hi, lo, sc = sdist.all_gather_bank(hi), sdist.all_gather_bank(lo), sdist.all_gather_bank(sc)
+                ev[1].record()
+                coll_ms["all_gather"].append(ev)
+            fe._mark(timers, "begin")
+            pairs, pscores, counts, _ = matchers.match((hi, lo), (hi, lo), variant, pair_index=pidx_local,
+                                                       mode=mode, scores1=sc, scores2=sc, **mkw)
+            fe._mark(timers, "match")
+            return f, pairs, pscores, counts
 
     replay = None
-    if not a.no_graph:
-        replay, g_feats, g_pairs, g_pscores, g_counts = fe.capture_sequence(sal, feat, matchers.M1, chunk=a.chunk,
-                                                                            ratio_thresh=0.8)
+    use_graph = not a.no_graph and not (a.kind == "allpairs" and world > 1)      # NCCL stays outside graphs
+    if use_graph:
+        replay, (g_feats, g_pairs, g_pscores, g_counts) = fe.capture(run)
+
+    npl = plan["npairs_local"] if plan["npairs_local"] is not None else int(pidx_local.shape[0])
+    pad_pairs = plan["pad_pairs"] if plan["pad_pairs"] is not None else pad
+    padded = None
+    if world > 1 and pad_pairs != npl:
+        padded = (torch.full((pad_pairs, K, 2), -1, dtype=torch.int32, device=dev),
+                  torch.zeros((pad_pairs, K), device=dev), torch.zeros((pad_pairs,), dtype=torch.int32, device=dev))
 
     def step(timers=None, eager=False):
         if replay is not None and not eager:
-            replay()                                         # one graph launch = the whole step
+            replay()
             pairs, pscores, counts = g_pairs, g_pscores, g_counts
         else:
-            feats, pairs, pscores, counts = fe.run_sequence(sal, feat, matchers.M1, chunk=a.chunk,
-                                                            timers=timers, ratio_thresh=0.8)
+            _, pairs, pscores, counts = run(timers)
         gathered = None
         if world > 1:
+            if padded is not None:                           # ranks own different numbers of pairs
+                for dst, src in zip(padded, (pairs, pscores, counts)):
+                    dst[:npl].copy_(src)
+                pairs, pscores, counts = padded
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
             gathered = sdist.gather_match_lists(pairs, pscores, counts, dst=0)
+            ev[1].record()
+            coll_ms["gather_lists"].append(ev)
         return pairs, pscores, counts, gathered
 
     def fence():
@@ -256,42 +491,35 @@ def run_b200(a):
     for _ in range(a.warmup):
         step()
     fence()
+    coll_ms = {k: [] for k in coll_ms}
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
-    launches0 = ops.launch_count()
-    launches_per_eager_step = None
-    if replay is not None:                                   # graph replays bypass the library's counter
-        c0 = ops.launch_count()
-        step(eager=True)
-        fence()
-        launches_per_eager_step = ops.launch_count() - c0
-        launches0 = ops.launch_count()
-    timer_lists = []
+    c0 = ops.launch_count()
+    step(eager=True)
+    fence()
+    launches_per_step = ops.launch_count() - c0              # graph replays bypass the library's counter
+    coll_ms = {k: [] for k in coll_ms}
     t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` sees only the timed steps
     t_beg.record()
     for _ in range(a.steps):
-        tl = []
-        out = step(tl)
-        timer_lists.append(tl)
+        out = step()
     t_end.record()
     fence()
     torch.cuda.profiler.stop()
     sampler.stop_flag = True
-    launches = ops.launch_count() - launches0
-    if launches_per_eager_step is not None:
-        launches = launches_per_eager_step * a.steps         # kernels inside the replayed graphs
     ms_total = t_beg.elapsed_time(t_end)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / a.steps
-    pairs_per_step = (T - 1) * world
+    pairs_per_step = plan["npairs_global"]
     value = pairs_per_step / (ms_step * 1e-3)
+    coll = {k: (sum(e0.elapsed_time(e1) for e0, e1 in v) / max(len(v), 1) if v else None) for k, v in coll_ms.items()}
+    final_pairs, final_scores, final_counts = (t.clone() for t in out[:3])
 
-    # instrumented pass: the same K steps again with a CUDA-event pair around every kernel launch of
-    # the library (sslam_profile_*), for the per-kernel roofline numbers
+    # ---- instrumented pass: CUDA events around every kernel launch of the library (per-kernel rooflines)
     ops.profile_enable(True)
     for _ in range(a.steps):
         step(eager=True)
@@ -299,37 +527,74 @@ def run_b200(a):
     kernel_ms = ops.profile_read()
     ops.profile_enable(False)
 
-    # per-stage device time from the event marks (same stream as the kernels)
-    stage_ms = {}
-    if replay is not None:                                   # stage marks need eager launches
-        timer_lists = []
-        for _ in range(a.steps):
-            tl = []
-            step(tl, eager=True)
-            timer_lists.append(tl)
-        fence()
+    # ---- per-stage device time from event marks (eager launches)
+    stage_ms, timer_lists = {}, []
+    for _ in range(a.steps):
+        tl = []
+        step(tl, eager=True)
+        timer_lists.append(tl)
+    fence()
     for tl in timer_lists:
         for (n0, e0), (n1, e1) in zip(tl[:-1], tl[1:]):
             if n1 != "begin":
                 stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1)
     stage_ms = {k: v / a.steps for k, v in stage_ms.items()}
 
-    # ---- e2e: host buffers -> match lists on host, through the public pipeline entry point
+    # ---- e2e: pinned host buffers -> match lists on the host, through the public entry points
     e2e = None
     if not a.no_e2e:
-        sal_h = torch.empty(sal.shape, dtype=sal.dtype, pin_memory=True).copy_(sal)
-        feat_h = torch.empty(feat.shape, dtype=feat.dtype, pin_memory=True).copy_(feat)
+        # bare pinned-copy probe: the same chunks, no kernels, all ranks at once = the H2D ceiling
+        stage = [torch.empty((a.e2e_chunk,) + tuple(sal_h.shape[1:]), device=dev),
+                 torch.empty((a.e2e_chunk,) + tuple(feat_h.shape[1:]), device=dev)]
+
+        def probe():
+            for s in range(0, Tl, a.e2e_chunk):
+                e = min(Tl, s + a.e2e_chunk)
+                stage[0][:e - s].copy_(sal_h[s:e], non_blocking=True)
+                stage[1][:e - s].copy_(feat_h[s:e], non_blocking=True)
+        probe()
+        fence()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(3):
+            probe()
+        p1.record()
+        fence()
+        probe_ms = p0.elapsed_time(p1) / 3
+        if world > 1:
+            t = torch.tensor([probe_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            probe_ms = float(t.item())
+        del stage
+
+        if a.kind == "sequence":
+            host_fn = lambda oh: fe.run_sequence_host(sal_h, feat_h, variant, chunk=a.e2e_chunk, out_host=oh, **mkw)  # noqa: E731
+        elif a.kind == "pairs":
+            host_fn = lambda oh: fe.run_pairs_host(sal_h, feat_h, pidx_local, variant, chunk=a.e2e_chunk, out_host=oh, **mkw)  # noqa: E731
+        else:
+            def host_fn(oh):                                  # H2D of the keyframes, device step, D2H of the lists
+                sal.copy_(sal_h, non_blocking=True)
+                feat.copy_(feat_h, non_blocking=True)
+                pr, ps, cn, _ = step(eager=True)
+                if oh is None:
+                    oh = tuple(torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (pr, ps, cn))
+                for d_, s_ in zip(oh, (pr, ps, cn)):
+                    d_.copy_(s_, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                return oh
         out_h = None
         for _ in range(max(1, min(2, a.warmup))):
-            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.e2e_chunk, out_host=out_h,
-                                         ratio_thresh=0.8)
+            out_h = host_fn(out_h)
         fence()
         w0 = time.perf_counter()
         e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e_beg.record()
         for _ in range(a.steps):
-            out_h = fe.run_sequence_host(sal_h, feat_h, matchers.M1, chunk=a.e2e_chunk, out_host=out_h,
-                                         ratio_thresh=0.8)
+            out_h = host_fn(out_h)
+            if world > 1 and a.kind != "allpairs":
+                # the lists of every rank are on its own host; the NCCL gather of the device arm is not part
+                # of the host-to-host path
+                pass
         e_end.record()
         fence()
         wall_ms = (time.perf_counter() - w0) * 1e3
@@ -339,10 +604,80 @@ def run_b200(a):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
         d2h = sum(t.numel() * t.element_size() for t in out_h)
-        e2e = {"value": pairs_per_step / (e_ms / a.steps * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e_ms / a.steps}
-        del sal_h, feat_h
+        e_step = e_ms / a.steps
+        e2e = {"value": pairs_per_step / (e_step * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": e_step,
+               "h2d_ceiling_gbs": in_bytes / (probe_ms * 1e-3) / 1e9,
+               "h2d_probe_ms": probe_ms, "frac_of_h2d_ceiling": probe_ms / e_step,
+               "note": "per rank; h2d_ceiling_gbs = bare pinned copies of the same staging chunks, no kernels, "
+                       "every rank at once; frac_of_h2d_ceiling = probe time / e2e step time"}
+
+    # ---- parity against the CPU arm on identical inputs
+    parity, cpu = None, None
+    if rank == 0:
+        gp = final_pairs.cpu().numpy()
+        gc = final_counts.cpu().numpy()
+        from oracle import pipeline as opipe
+        gkp = (g_feats["keypoints_pixel"] if replay is not None else run()[0]["keypoints_pixel"]).cpu().numpy()
+
+        def gpu_record(p):                                    # consecutive pair p = frames (p, p + 1)
+            return opipe.pair_record(gp[p, :int(gc[p])], gkp[p], gkp[p + 1])
+        cores = opipe.host_cores()
+        if a.kind == "sequence" and not a.no_cpu_baseline and (world == 1 or a.scaling == "strong"):
+            # rank 0 holds the first frames of sequence 0 in both scaling modes
+            frames = a.cpu_sample_frames or (min(a.frames, Tl) if a.workload == "c2" else 9)
+            frames = min(frames, Tl)
+            v, sec, rec, kind = cpu_pipeline(a, frames, cores)
+            same_n = sum(1 for p, r in enumerate(rec) if gpu_record(p)[0] == r[0])
+            same_l = sum(1 for p, r in enumerate(rec) if gpu_record(p) == tuple(r))
+            parity = {"pairs": len(rec), "identical_counts": same_n, "identical_lists": same_l,
+                      "max_count_delta": max(abs(gpu_record(p)[0] - r[0]) for p, r in enumerate(rec)),
+                      "against": kind, "note": "match lists compared by count and by CRC32 of the sorted (x1,y1,x2,y2) keypoint rows (independent "
+                                               "of torch.topk's unspecified order of equal scores); lists may differ only by similarity "
+                                               "near ties (tests/: margins < 2*(eps+2e-6))"}
+            if world == 1:
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                       "sample": cpu_sample_text(kind, frames, cores, sec)}
+        elif not a.no_cpu_baseline and world == 1:
+            # pairs / all-pairs: the oracle on a bounded sample of the same frames
+            import oracle
+            nfr = 4 if a.kind == "pairs" else 5
+            w = oracle.RefinerWeights.from_state_dict(refiner.state_dict())
+            t0 = time.perf_counter()
+            okp, osc, _ = oracle.select_keypoints(sal_h[:nfr].numpy(), K)
+            od = oracle.refiner_forward(w, oracle.extract_at_keypoints(feat_h[:nfr].numpy(), oracle.pixel_to_patch(okp)))
+            if a.kind == "pairs":
+                plist = [(2 * p, 2 * p + 1, p) for p in range(nfr // 2)]
+            else:
+                lut = {tuple(r): i for i, r in enumerate(pidx_local.cpu().tolist())}
+                plist = [(i, j, lut[(i, j)]) for i in range(nfr) for j in range(i + 1, nfr)]
+            agree, refn = 0, 0
+            for (i, j, p) in plist:
+                if a.kind == "pairs":
+                    ref = {(x, y) for x, y, _ in oracle.match_m1(od[i], od[j], 0.8)}
+                else:
+                    ref = {tuple(r) for r in oracle.match_m2(od[i], od[j], osc[i], osc[j])[0].tolist()}
+                got = {tuple(r) for r in gp[p, :int(gc[p])].tolist()}
+                agree += len(ref & got)
+                refn += len(ref | got)
+            sec = time.perf_counter() - t0
+            parity = {"pairs": len(plist), "index_agreement": agree / max(refn, 1), "against": "port",
+                      "note": "oracle end to end on its own descriptors for the first frames; "
+                              + ("bf16 similarity: agreement is a percentage by design" if a.mode_name == "bf16" else
+                                 "fp32 mode")}
+            cpu = {"value": len(plist) / sec, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{nfr} frames / {len(plist)} pairs of the same workload, oracle port (NumPy), single process, {sec:.1f} s"}
+
+    eager = None
+    if rank == 0 and not a.no_eager_baseline:
+        try:
+            v = gpu_eager_baseline(a, sal, feat, refiner)
+            eager = {"value": v, "unit": UNIT, "kind": "torch_eager_restatement",
+                     "sample": "first 16 frames / 15 consecutive pairs, stock PyTorch ops on the same B200 "
+                               "(quantile, max_pool2d, topk, grid_sample, cuBLAS fp32 linear + layer_norm, mm, argmax), "
+                               "per-frame launches as the reference issues them"}
+        except Exception as e:                               # pragma: no cover
+            eager = {"value": None, "error": repr(e)[:200]}
 
     if rank != 0:
         if world > 1:
@@ -352,21 +687,20 @@ def run_b200(a):
     peaks, peak_src = measured_peaks()
     peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     hbm = float(peaks["hbm_gbs"])
-    rows = T * a.kpts
+    rows = Tl * K
     blocks = 2
-    work = {   # algorithmic work per step of each kernel kind
-        "gemm_f16x3": ("tensor", 2.0 * rows * (C * 384 + blocks * 2 * 384 * 384 + 384 * D)),
-        "match_tc": ("tensor", 2.0 * a.kpts * a.kpts * D * (T - 1)),
-        "match_f32": ("tensor", 2.0 * a.kpts * a.kpts * D * (T - 1)),
-        "decode_scan": ("hbm", (4.0 * H * W + 12 * a.kpts) * T),
-        "gather": ("hbm", (4.0 * (H // 16) * (W // 16) * C + 8 * a.kpts + 4 * a.kpts * C) * T),
-        "l2norm": ("hbm", 8.0 * a.kpts * D * T),
-        "layernorm": ("hbm", 8.0 * rows * 384 * 2 * blocks),
+    mm_flops = 2.0 * K * K * D * npl
+    work = {   # algorithmic work per step on this rank
+        "gemm_f16x3": ("tensor", 2.0 * rows * (C * HID + blocks * 2 * HID * HID + HID * D)),
+        "match_tc": ("tensor", mm_flops), "match_f32": ("tensor", mm_flops),
+        "decode_scan": ("hbm", (4.0 * a.H * a.W + 12 * K) * Tl),
+        "gather": ("hbm", (4.0 * (a.H // 16) * (a.W // 16) * C + 8 * K + 4 * K * C) * Tl),
+        "l2norm": ("hbm", 8.0 * K * D * Tl),
     }
     kernels = {}
     for kind, (ms_tot, n) in kernel_ms.items():
         e = {"ms_per_step": ms_tot / a.steps, "launches_per_step": n / a.steps}
-        if kind in work:
+        if kind in work and e["ms_per_step"] > 0:
             bound, w = work[kind]
             if bound == "tensor":
                 e["algorithmic_TFLOP/s"] = w / (e["ms_per_step"] * 1e-3) / 1e12
@@ -377,22 +711,21 @@ def run_b200(a):
         kernels[kind] = e
     dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
     dk = kernels[dom]
-    # dram bytes per launch from the committed `ncu --set full` capture (profiles/), where available
-    ncu_traffic = {"gemm_f16x3": NCU_GEMM_DRAM_BYTES_PER_ROW * rows / (dk["launches_per_step"] / 6.0)
-                   if dom == "gemm_f16x3" else None}
-    tf32_note = ("fp32 accuracy costs three 16-bit MMAs per product (fp16 hi/lo split), so the ceiling of "
-                 "this fraction is 1/3 = 0.333 (1/6 for the tf32x3 variant)")
+    split_note = ("fp32 accuracy costs three 16-bit MMAs per product (fp16 hi/lo split), so the ceiling of "
+                  "this fraction is 1/3 = 0.333 (1/6 for the tf32x3 variant)")
     if work.get(dom, ("", 0))[0] == "tensor":
         ach = dk["algorithmic_TFLOP/s"]
+        traffic = ncu_traffic(dom, rows / max(dk["launches_per_step"] / 6.0, 1e-9)) if dom == "gemm_f16x3" else None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": ncu_traffic.get(dom),
+                    "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src + ", bf16 dense sustained",
                     "launch_ms": dk["ms_per_step"] / dk["launches_per_step"],
                     "launches_per_step": dk["launches_per_step"],
                     "algorithmic_flops_per_step": work[dom][1],
                     "note": ("achieved = algorithmic flops of all launches of this kernel in a step / their "
-                             "summed CUDA-event durations (instrumented pass of the same steps); "
-                             + (tf32_note if mode_name != "bf16" or dom == "gemm_f16x3" else ""))}
+                             "summed CUDA-event durations (instrumented pass of the same steps); traffic = dram bytes per "
+                             "launch from profiles/ncu_traffic.json (null when no capture of this kernel is on file); "
+                             + (split_note if (a.mode_name != "bf16" or dom == "gemm_f16x3") else ""))}
     else:
         ach = dk.get("algorithmic_GB/s", float("nan"))
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s",
@@ -400,28 +733,24 @@ def run_b200(a):
                     "launch_ms": dk["ms_per_step"] / dk["launches_per_step"]}
     stages = {k: {"ms_per_step": v} for k, v in stage_ms.items()}
 
-    cpu = None
-    if world == 1 and not a.no_cpu_baseline:
-        from oracle import pipeline as opipe
-        cores = opipe.host_cores()
-        frames = max(3, a.cpu_sample_frames)
-        v, sec, npairs = cpu_pipeline_rate(a, frames, cores)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{frames} frames / {npairs} pairs of the same workload, oracle port "
-                         f"(NumPy) in a {cores}-process pool, {sec:.1f} s"}
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"f32": "f32", "tf32x3": "tf32x3 (fp32 in/out)", "f16x3": "f16x3 (fp32 in/out)", "bf16": "bf16"}[mode_name],
-            "data": "synthetic",
-            "config": {"workload": workload_name(a), "frames_per_rank": T, "pairs_per_step": pairs_per_step,
-                       "similarity_mode": mode_name, "chunk": a.chunk, "e2e_chunk": a.e2e_chunk,
-                       "launch": "CUDA graph replay (one graph per step)" if replay is not None else "eager",
-                       "l2_policy": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)",
-                       "parallelism": f"{world} independent sequence shard(s), final NCCL gather of match lists"
-                       if world > 1 else "single GPU"},
-            "roofline": roofline, "kernels": kernels, "stages": stages, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": sampler.summary()}
+    cfg = workload_config(a)
+    line = {"metric": METRIC if a.workload == "c2" else f"frame-pairs/sec extract+match, workload {a.workload}",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": a.scaling,
+            "vs_baseline": None,
+            "dtype": {"f32": "f32", "tf32x3": "tf32x3 (fp32 in/out)", "f16x3": "f16x3 (fp32 in/out)", "bf16": "bf16"}[a.mode_name],
+            "data": "synthetic", "config": cfg,
+            "run": {"frames_per_rank": Tl, "pairs_per_step": pairs_per_step, "pairs_this_rank": npl,
+                    "similarity_mode": a.mode_name, "chunk": a.chunk, "e2e_chunk": a.e2e_chunk,
+                    "launch": "CUDA graph replay (one graph per step)" if replay is not None else "eager",
+                    "l2_policy": f"inputs larger than L2 ({in_bytes / 1e6:.0f} MB per step per GPU)",
+                    "parallelism": (f"{world} ranks, {a.scaling} scaling, one packed NCCL gather of match records"
+                                    + (", NCCL all-gather of descriptor banks" if a.kind == "allpairs" else ""))
+                    if world > 1 else "single GPU",
+                    "collective_ms_per_step": coll},
+            "roofline": roofline, "kernels": kernels, "stages": stages, "parity": parity, "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager, "e2e": e2e,
+            "gpu_launches": int(launches_per_step * a.steps), "clocks": sampler.summary()}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -12,6 +12,7 @@ host core (the reference itself is single-process Python with intra-op BLAS thre
 
 import os
 import time
+import zlib
 from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
@@ -53,14 +54,26 @@ def _extract_job(args):
     return extract_frame(sal, feat, _W["weights"], K)
 
 
+def pair_record(ij, kp1, kp2):
+    """(count, crc32) of a match list in a form that does not depend on the ORDER of equal-score
+    keypoints (``torch.topk`` leaves it unspecified): every match (i, j) becomes
+    the int32 row (x1, y1, x2, y2) of its two keypoints and the rows are sorted.  Lets bench.py
+    compare whole lists between implementations, not just counts."""
+    ij = np.asarray(ij, dtype=np.int64).reshape(-1, 2)
+    rows = np.concatenate([np.asarray(kp1)[ij[:, 0]], np.asarray(kp2)[ij[:, 1]]], axis=1).astype(np.int32)
+    rows = rows[np.lexsort(rows.T[::-1])] if rows.shape[0] else rows
+    return int(rows.shape[0]), zlib.crc32(np.ascontiguousarray(rows).tobytes())
+
+
 def _match_job(args):
-    variant, d1, d2, s1, s2 = args
+    variant, d1, d2, s1, s2, kp1, kp2 = args
     r = match_pair(variant, d1, d2, s1, s2)
-    return len(r) if isinstance(r, list) else r[0].shape[0]
+    ij = [(i, j) for i, j, _ in r] if isinstance(r, list) else r[0]
+    return pair_record(ij, kp1, kp2)
 
 
 def run_sequence(sal, feat, weights, K, variant=1, workers=1):
-    """sal (T,H,W) fp32, feat (T,h,w,C) fp32 -> (per-pair match counts, seconds).
+    """sal (T,H,W) fp32, feat (T,h,w,C) fp32 -> (per-pair (match count, crc32 of the pair list), seconds).
     workers > 1 distributes frames, then pairs, over that many processes (1 BLAS thread each)."""
     T = sal.shape[0]
     t0 = time.perf_counter()
@@ -68,15 +81,14 @@ def run_sequence(sal, feat, weights, K, variant=1, workers=1):
         ex = [extract_frame(sal[t], feat[t], weights, K) for t in range(T)]
         counts = []
         for t in range(T - 1):
-            r = match_pair(variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1])
-            counts.append(len(r) if isinstance(r, list) else r[0].shape[0])
+            counts.append(_match_job((variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1], ex[t][0], ex[t + 1][0])))
     else:
         with ProcessPoolExecutor(workers, initializer=_init_worker,
                                  initargs=(weights.p, 1)) as pool:
             t0 = time.perf_counter()                      # pool start-up is not the algorithm
             ex = list(pool.map(_extract_job, [(sal[t], feat[t], K) for t in range(T)]))
-            counts = list(pool.map(_match_job, [(variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1])
-                                                for t in range(T - 1)]))
+            counts = list(pool.map(_match_job, [(variant, ex[t][2], ex[t + 1][2], ex[t][1], ex[t + 1][1],
+                                                 ex[t][0], ex[t + 1][0]) for t in range(T - 1)]))
     return counts, time.perf_counter() - t0
 
 

@@ -129,6 +129,88 @@ class FrontEnd:
         pairs, pscores, counts = self.match_consecutive(feats, variant, timers=timers, **kw)
         return feats, pairs, pscores, counts
 
+    @torch.no_grad()
+    def run_pairs(self, saliency, features, pair_index, variant=matchers.M1, chunk=256, timers=None, **kw):
+        """Extract every frame once (in chunks) into a resident bank and match the listed (a, b)
+        frame pairs (independent pairs, all-pairs / loop-closure lists).  Returns
+        (feats, pairs, pair_scores, counts), all on device."""
+        T = saliency.shape[0]
+        feats = self._alloc_bank(T, saliency.device)
+        for s in range(0, T, chunk):
+            e = min(T, s + chunk)
+            self.extract(saliency[s:e], features[s:e], timers=timers, out=self._bank_slice(feats, s, e))
+        if self.grid != "pixel":
+            feats["keypoints_pixel"] = feats["keypoints"] * self.patch + self.patch / 2
+        self._mark(timers, "begin")
+        pairs, pscores, counts = self.match_pairs(feats, pair_index, variant, **kw)
+        self._mark(timers, "match")
+        return feats, pairs, pscores, counts
+
+    @torch.no_grad()
+    def capture(self, fn, *args, **kw):
+        """Capture ``fn(*args, **kw)`` (run_sequence / run_pairs on static input tensors) into a CUDA
+        graph after two warm-up calls on a side stream.  Returns (replay, results of fn)."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn(*args, **kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fn(*args, **kw)
+        return graph.replay, out
+
+    @torch.no_grad()
+    def run_pairs_host(self, saliency_host, features_host, pair_index, variant=matchers.M1, chunk=64,
+                       out_host=None, **kw):
+        """End-to-end entry point for HOST data and a pair LIST: pinned (T,H,W,1) saliency and
+        (T,h,w,C) features stream to the device chunk by chunk (double-buffered on a copy stream,
+        overlapping the extraction of the previous chunk); when every frame is resident the listed
+        pairs are matched and the lists copied back.  Returns host tensors (pairs, scores, counts)."""
+        dev = torch.device("cuda", torch.cuda.current_device())
+        T = saliency_host.shape[0]
+        compute = torch.cuda.current_stream()
+        st, copy = self._staging(saliency_host, features_host, chunk, dev)
+        feats = self._alloc_bank(T, dev)
+        copy.wait_stream(compute)
+        for ci, s in enumerate(range(0, T, chunk)):
+            e = min(T, s + chunk)
+            b = ci & 1
+            with torch.cuda.stream(copy):
+                if ci >= 2:
+                    copy.wait_event(st["free"][b])
+                st["sal"][b][:e - s].copy_(saliency_host[s:e], non_blocking=True)
+                st["feat"][b][:e - s].copy_(features_host[s:e], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(copy)
+            compute.wait_event(ready)
+            self.extract(st["sal"][b][:e - s], st["feat"][b][:e - s], out=self._bank_slice(feats, s, e))
+            st["free"][b].record(compute)
+        res = self.match_pairs(feats, pair_index, variant, **kw)
+        P = pair_index.shape[0]
+        if out_host is None:
+            out_host = (torch.empty((P, self.K, 2), dtype=torch.int32, pin_memory=True),
+                        torch.empty((P, self.K), dtype=torch.float32, pin_memory=True),
+                        torch.empty((P,), dtype=torch.int32, pin_memory=True))
+        for dst, src in zip(out_host, res):
+            dst.copy_(src, non_blocking=True)
+        compute.synchronize()
+        return out_host
+
+    def _staging(self, saliency_host, features_host, chunk, dev):
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._stage = {}
+        key = (tuple(saliency_host.shape[1:]), tuple(features_host.shape[1:]), chunk)
+        if self._stage.get("key") != key:
+            self._stage = dict(key=key,
+                               sal=[torch.empty((chunk,) + tuple(saliency_host.shape[1:]), device=dev) for _ in range(2)],
+                               feat=[torch.empty((chunk,) + tuple(features_host.shape[1:]), device=dev) for _ in range(2)],
+                               free=[torch.cuda.Event(), torch.cuda.Event()])
+        return self._stage, self._copy_stream
+
     def _alloc_bank(self, T, device):
         """Resident per-sequence bank the chunked extraction writes into (no concatenation)."""
         D = self.refiner.output_dim
@@ -180,17 +262,7 @@ class FrontEnd:
         dev = torch.device("cuda", torch.cuda.current_device())
         T = saliency_host.shape[0]
         compute = torch.cuda.current_stream()
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream()
-            self._stage = {}
-        copy = self._copy_stream
-        key = (tuple(saliency_host.shape[1:]), tuple(features_host.shape[1:]), chunk)
-        if self._stage.get("key") != key:
-            self._stage = dict(key=key,
-                               sal=[torch.empty((chunk,) + tuple(saliency_host.shape[1:]), device=dev) for _ in range(2)],
-                               feat=[torch.empty((chunk,) + tuple(features_host.shape[1:]), device=dev) for _ in range(2)],
-                               free=[torch.cuda.Event(), torch.cuda.Event()])
-        st = self._stage
+        st, copy = self._staging(saliency_host, features_host, chunk, dev)
         feats = self._alloc_bank(T, dev)
         if out_host is None:
             out_host = (torch.empty((T - 1, self.K, 2), dtype=torch.int32, pin_memory=True),
