@@ -409,7 +409,8 @@ def run_b200(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     mode = {"f32": ops.SIM_F32, "tf32x3": ops.SIM_TF32X3, "bf16": ops.SIM_BF16, "f16x3": ops.SIM_F16X3}[a.mode_name]
     variant = matchers.M2 if a.kind == "allpairs" else matchers.M1
     mkw = {} if a.kind == "allpairs" else {"ratio_thresh": 0.8}
@@ -464,12 +465,14 @@ def run_b200(a):
         padded = (torch.full((pad_pairs, K, 2), -1, dtype=torch.int32, device=dev),
                   torch.zeros((pad_pairs, K), device=dev), torch.zeros((pad_pairs,), dtype=torch.int32, device=dev))
 
+    last_feats = [g_feats if replay is not None else None]
+
     def step(timers=None, eager=False):
         if replay is not None and not eager:
             replay()
             pairs, pscores, counts = g_pairs, g_pscores, g_counts
         else:
-            _, pairs, pscores, counts = run(timers)
+            last_feats[0], pairs, pscores, counts = run(timers)
         gathered = None
         if world > 1:
             if padded is not None:                           # ranks own different numbers of pairs
@@ -618,7 +621,7 @@ def run_b200(a):
         gp = final_pairs.cpu().numpy()
         gc = final_counts.cpu().numpy()
         from oracle import pipeline as opipe
-        gkp = (g_feats["keypoints_pixel"] if replay is not None else run()[0]["keypoints_pixel"]).cpu().numpy()
+        gkp = last_feats[0]["keypoints_pixel"].cpu().numpy()      # (no collective may run on rank 0 alone)
 
         def gpu_record(p):                                    # consecutive pair p = frames (p, p + 1)
             return opipe.pair_record(gp[p, :int(gc[p])], gkp[p], gkp[p + 1])

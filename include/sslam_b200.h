@@ -240,6 +240,25 @@ int sslam_eval_matches(const int32_t* pred, const int32_t* pred_counts, int pred
 int sslam_heatmap_from_cells_f32(const float* logits, int B, int Hc, int Wc, int cell, int border,
                                  float* heat, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * KeypointSelector head (models/keypoint_selector.py:30-34, 56-65): Conv2d(C, hidden, 3, padding=1)
+ * -> ReLU -> Conv2d(hidden, 1, 1) [-> sigmoid] on the NHWC patch-feature map, as one tcgen05
+ * implicit-GEMM kernel (f16x3: fp32-level accuracy) whose epilogue contracts the hidden activations
+ * with the 1x1 convolution; writes one value per pixel.
+ *   feat [B,H,W,C] fp32 NHWC;  packed = sslam_selector_pack_weights(conv.0.weight [hidden,C,3,3]);
+ *   conv1_bias [hidden], conv2_weight [hidden] (= conv.2.weight [1,hidden,1,1]), conv2_bias [1]: fp32
+ *   out [B,H,W] fp32: logits (apply_sigmoid = 0) or saliency (1).
+ * C % 64 == 0, hidden % 8 == 0, hidden <= 512.
+ */
+size_t sslam_selector_packed_bytes(int C, int hidden);
+int sslam_selector_pack_weights(const float* conv1_weight, int C, int hidden, void* packed,
+                                size_t packed_bytes, void* stream);
+size_t sslam_selector_workspace_bytes(int B, int H, int W, int C);
+int sslam_selector_head_f32(const float* feat, const void* packed, const float* conv1_bias,
+                            const float* conv2_weight, const float* conv2_bias, int B, int H, int W,
+                            int C, int hidden, int apply_sigmoid, float* out, void* ws,
+                            size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,10 @@ void sslam_debug_gemm_stalls(long long* buf);
  * mbarrier waits that timed out in the GEMM translation unit; returns a cudaError_t value. */
 int sslam_debug_watchdog_gemm(unsigned long long* buf);
 
+/* 0: force the register-prefetching decode scan + radix-select top-k (the fallback kernels for maps the
+ * streaming scan does not take); non-zero (default): streaming scan + histogram top-k where eligible. */
+void sslam_debug_decode_stream(int on);
+
 #ifdef __cplusplus
 }
 #endif

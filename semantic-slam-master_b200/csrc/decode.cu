@@ -3,11 +3,23 @@
 // Replaces KeypointSelector.select_keypoints/_apply_nms (models/keypoint_selector.py:69-226).
 //
 // Data flow (per call, all images in every launch):
-//   K1 scan     : one DRAM read of the map, smem-tiled (2r+1)^2 NMS, local maxima appended to a
-//                 per-image candidate list as 64-bit keys (score bits << 32 | ~linear index)
-//   K2 topk     : per image, exact K-th largest key (adaptive radix select), compaction, bitonic
-//                 sort in smem -> tentative main-branch output (score desc, index asc)
-//   K3 count    : second pass over the map (L2 resident): how many pixels are < the K-th score
+//   K1 scan     : ONE DRAM read of the map.  Row slabs stream through a shared-memory ring (bulk async
+//                 copies, mbarrier pipeline: the bytes in flight per SM no longer depend on registers),
+//                 (2r+1)^2 NMS from a rolling register window, local maxima appended to a per-image
+//                 candidate list as 64-bit keys (score bits << 32 | ~linear index) and binned into a
+//                 per-image 1024-bin score histogram; while the pixels are in registers the kernel also
+//                 counts those below a speculative threshold t_b (see K3)
+//   K2 topk     : per image, the histogram locates the bin of the K-th candidate, ONE pass over the
+//                 candidate list keeps the keys at or above that bin (K + a few hundred) in shared
+//                 memory, bitonic sort -> tentative main-branch output (score desc, index asc), the
+//                 K-th key and the count of boundary ties.  (Plateau maps whose boundary bin overflows
+//                 the buffer take an exact radix select over the whole list instead.)
+//   K3 count    : how many pixels are < the K-th score.  The scan already counted the pixels below
+//                 t_b; when t_b <= K-th score that count is a lower bound and usually proves the main
+//                 branch, and this kernel exits without touching the map.  Only images whose
+//                 speculation failed are read a second time.  t_b is a hint kept in the workspace
+//                 (0.95 x the image slot's last K-th score): it never changes a result, only whether
+//                 the second pass is needed.
 //   K4 resolve  : the main branch (keypoint_selector.py:120-128) is taken iff at least K NMS
 //                 survivors exceed thr = max(quantile(map, p), floor).  Because the quantile lies
 //                 between order statistics v[lo] <= thr32 <= v[hi], "count(pixels < kth score) >
@@ -20,6 +32,7 @@
 #include "common.cuh"
 
 namespace sslam {
+bool g_decode_no_stream = false;         // tools / tests: force the register-prefetching scan kernels
 namespace {
 
 constexpr int TILE_W = 128;
@@ -27,6 +40,7 @@ constexpr int TILE_H = 32;
 constexpr int MAX_R = 8;
 constexpr int SCAN_THREADS = 256;
 constexpr int SEL_THREADS = 1024;
+constexpr int RES_THREADS = 512;       // resolve: 128 registers per thread available, no spills
 constexpr float LOWER_FLOOR = 0.05f;     // keypoint_selector.py:141
 
 struct __align__(16) ImgHeader {
@@ -35,8 +49,15 @@ struct __align__(16) ImgHeader {
   u64 kth_key;         // K-th largest candidate key (K2); 0 when fewer than K candidates
   u32 have_tentative;  // K2 wrote a tentative main-branch result
   u32 ties;            // candidates equal to the K-th score left unselected
-  u32 pad[2];
+  u32 spec_below;      // pixels strictly below the speculative threshold hint[b] (K1)
+  u32 pad;
 };
+
+constexpr int HIST_BINS = 1024;          // candidate scores in [2^-8, 1): 8 binades x 128 bins
+__device__ __forceinline__ int score_bin(u32 score_bits) {           // monotone for positive scores
+  const int b = (int)(score_bits >> 16) - 0x3b80;
+  return b < 0 ? 0 : (b > HIST_BINS - 1 ? HIST_BINS - 1 : b);
+}
 
 struct DecodeParams {
   const float* sal;
@@ -47,6 +68,8 @@ struct DecodeParams {
   float* scores;
   int32_t* info;
   ImgHeader* hdr;
+  float* hint;         // [B] speculative count thresholds; persists across calls in the workspace
+  u32* chist;          // [B][HIST_BINS] candidate score histogram (stream scan only), or null
   u64* cand;           // [B][H*W]
 };
 
@@ -331,6 +354,174 @@ __global__ void __launch_bounds__(256) decode_scan_vec_kernel(DecodeParams p, in
   for (u32 i = threadIdx.x; i < nstaged; i += blockDim.x) cand[sbase + i] = sbuf[i];
 }
 
+// K1, streaming path (radius 1..3, W % 4 == 0, 16-byte aligned maps, W <= 1800): the arithmetic of the
+// vector kernel above, fed from shared memory.  A CTA owns a band of output rows of one image over
+// the full width; a producer warp streams the band (plus R halo rows each side) through a ring of
+// NS stages of WIN = 2R+1 rows with 1-D bulk async copies (rows of a band are contiguous), each
+// completing on the stage's `full` mbarrier; consumer warp w owns the 120-column strip w, reads its
+// lane's float4 of every row from the stage, and arrives on the stage's `empty` mbarrier when done
+// with it.  Bytes in flight per SM = stages x CTAs, independent of register count (the register-
+// prefetching kernel had 16 warps x 5 rows = 40 KB per SM in flight and reached 0.22 of HBM peak).
+// Also fills the candidate score histogram and the speculative below-threshold count.
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_wait(u32 bar, u32 parity) {
+  u32 ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+  }
+}
+
+constexpr int STREAM_MAX_WARPS = 15;     // consumer warps = strips of 120 columns
+
+template <int R>
+__global__ void __launch_bounds__(32 * (STREAM_MAX_WARPS + 1))
+decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows, int NS) {
+  constexpr int WIN = 2 * R + 1, OUTW = 120, CAP = 2048;
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ u64 sbuf[CAP];
+  __shared__ u32 shist[HIST_BINS];
+  __shared__ __align__(8) unsigned long long bars[2 * 16];     // full[NS], empty[NS]  (NS <= 16)
+  __shared__ u32 scount, sbase;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int H = p.H, W = p.W;
+  const int b = blockIdx.x / nbands, band = blockIdx.x - b * nbands;
+  const int y0 = band * band_rows, y1 = min(H, y0 + band_rows);
+  const int first = y0 - R, y_end = y1 + R;                   // rows [first, y_end) enter the window
+  const int nstage = (y_end - first + WIN - 1) / WIN;
+  const size_t img = (size_t)b * H * W;
+  const size_t stage_bytes = (size_t)WIN * W * 4;
+  const u32 full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[16]);
+
+  for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) shist[i] = 0;
+  if (threadIdx.x == 0) {
+    scount = 0;
+    for (int s = 0; s < NS; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(full0 + 8 * s) : "memory");
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(empty0 + 8 * s), "r"(nstrips) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == nstrips) {
+    // ---- producer: stage s holds rows first + s*WIN .. +WIN-1; rows outside the image are not
+    // loaded (the consumers mask them by index)
+    if (lane == 0) {
+      for (int s = 0; s < nstage; ++s) {
+        const int slot = s % NS;
+        if (s >= NS) bar_wait(empty0 + 8 * slot, ((s / NS) - 1) & 1);
+        const int r0 = first + s * WIN;
+        const int a = max(r0, 0), e = min(min(r0 + WIN, H), y_end);
+        const u32 bytes = e > a ? (u32)(e - a) * (u32)W * 4u : 0u;
+        const u32 bar = full0 + 8 * slot;
+        if (bytes) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          const u32 dst = smem_addr(dsm + slot * stage_bytes + (size_t)(a - r0) * W * 4);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst), "l"(p.sal + img + (size_t)a * W), "r"(bytes), "r"(bar) : "memory");
+        } else {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+      }
+    }
+  } else if (warp < nstrips) {
+    // ---- consumer warp = one 120-column strip
+    const int x = warp * OUTW - 4 + 4 * lane;                 // first of this lane's four columns
+    const bool col_ok = (x >= 0) && (x < W);                  // W % 4 == 0: all four or none
+    const bool out_lane = (lane >= 1) && (lane <= 30) && col_ok;
+    const float NEG_INF = __int_as_float(0xff800000);
+    const float min_keep = fminf(p.floor, LOWER_FLOOR);
+    // speculative count: pixels of output rows / output lanes below hint[b] (counted exactly once)
+    const float tspec = out_lane ? p.hint[b] : NEG_INF;
+    u32 below = 0;
+    ImgHeader* hdr = p.hdr + b;
+    u64* cand = p.cand + (size_t)b * H * W;
+    float hwin[WIN][4], cwin[WIN][4];                          // rings: row maxima / centre values
+#pragma unroll
+    for (int i = 0; i < WIN; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { hwin[i][c] = NEG_INF; cwin[i][c] = NEG_INF; }
+
+    for (int s = 0; s < nstage; ++s) {
+      const int slot = s % NS;
+      bar_wait(full0 + 8 * slot, (s / NS) & 1);
+      const unsigned char* st = dsm + slot * stage_bytes;
+      const int yy = first + s * WIN;
+#pragma unroll
+      for (int u = 0; u < WIN; ++u) {
+        const int yc = yy + u;
+        if (yc < y_end) {                                      // warp-uniform
+          float4 v4 = make_float4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
+          if (col_ok && yc >= 0 && yc < H) {
+            v4 = *reinterpret_cast<const float4*>(st + ((size_t)u * W + x) * 4);
+            if (p.from_logits) { v4.x = sigmoid_f32(v4.x); v4.y = sigmoid_f32(v4.y); v4.z = sigmoid_f32(v4.z); v4.w = sigmoid_f32(v4.w); }
+          }
+          float e[4 + 2 * R];
+          const float own[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) e[R + c] = own[c];
+#pragma unroll
+          for (int d = 0; d < R; ++d) {
+            e[d] = __shfl_up_sync(0xffffffffu, own[4 - R + d], 1);
+            e[R + 4 + d] = __shfl_down_sync(0xffffffffu, own[d], 1);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            float hm = e[c];
+#pragma unroll
+            for (int d = 1; d < WIN; ++d) hm = fmaxf(hm, e[c + d]);
+            hwin[u][c] = hm;
+            cwin[u][c] = own[c];
+          }
+          const int yo = yc - R;                               // output row whose window is complete
+          if (yo >= y0) {                                      // warp-uniform
+            unsigned mask = 0;
+            float cv[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              float m = hwin[0][c];
+#pragma unroll
+              for (int i = 1; i < WIN; ++i) m = fmaxf(m, hwin[i][c]);
+              cv[c] = cwin[(u + WIN - R) % WIN][c];
+              below += (cv[c] < tspec) ? 1u : 0u;
+              if (out_lane && (cv[c] == m) && (cv[c] > min_keep)) mask |= 1u << c;
+            }
+            while (mask) {                                     // sparse: ~4 % of the pixels
+              const int c = __ffs((int)mask) - 1;
+              mask &= mask - 1;
+              const float val = c == 0 ? cv[0] : c == 1 ? cv[1] : c == 2 ? cv[2] : cv[3];
+              const u32 lin = (u32)(yo * W + x + c);
+              const u32 bits = __float_as_uint(val);
+              const u64 key = ((u64)bits << 32) | (u64)(0xffffffffu - lin);
+              atomicAdd(&shist[score_bin(bits)], 1u);
+              const u32 pos = atomicAdd(&scount, 1u);
+              if (pos < (u32)CAP) sbuf[pos] = key;
+              else cand[atomicAdd(&hdr->cand_count, 1u)] = key;   // staging list full (plateau maps)
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+    }
+    below = warp_reduce_sum(below);
+    if (lane == 0 && below) atomicAdd(&hdr->spec_below, below);
+  }
+  __syncthreads();
+  const u32 nstaged = min(scount, (u32)CAP);
+  if (threadIdx.x == 0 && nstaged) sbase = atomicAdd(&p.hdr[b].cand_count, nstaged);
+  __syncthreads();
+  u64* cand = p.cand + (size_t)b * H * W;
+  for (u32 i = threadIdx.x; i < nstaged; i += blockDim.x) cand[sbase + i] = sbuf[i];
+  u32* gh = p.chist + (size_t)b * HIST_BINS;
+  for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) {
+    const u32 h = shist[i];
+    if (h) atomicAdd(gh + i, h);
+  }
+}
+
 // Plain NMS output (drop-in for _apply_nms)
 __global__ void __launch_bounds__(SCAN_THREADS) nms_kernel(const float* sal, int H, int W, int r,
                                                            float* out) {
@@ -447,6 +638,97 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_topk_kernel(DecodeParams p
   if (threadIdx.x == 0) { hdr->kth_key = kth; hdr->have_tentative = 1; hdr->ties = eq_total; }
 }
 
+// K2, histogram-guided: the stream scan binned every candidate's score into chist[b][1024].  A suffix
+// sum from the top bin finds the bin of the K-th candidate; one pass over the candidate list keeps
+// the keys at or above that bin in shared memory (K plus the population of the boundary bin) and a
+// bitonic sort orders them.  256 threads and ~K*16 bytes of shared memory per CTA: several images
+// per SM are in flight (the per-image work is a chain of block-wide barriers, so residency, not
+// issue slots, sets its throughput; the 1024-thread kernel below ran one image per SM).
+// Falls back to the exact radix select over the whole list when the boundary bin overflows `cap`.
+constexpr int TOPK2_THREADS = 256;
+
+__global__ void __launch_bounds__(TOPK2_THREADS) decode_topk_hist_kernel(DecodeParams p, int cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  u64* buf = reinterpret_cast<u64*>(smem_raw);                        // [cap], cap = pow2 >= 2K
+  __shared__ u32 wsum[TOPK2_THREADS / 32];
+  __shared__ u32 counter, cut_bin, list_len, eq_total;
+  __shared__ SelectScratch ss_fallback;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ImgHeader* hdr = p.hdr + b;
+  const int n = (int)hdr->cand_count;
+  if (n < p.K) {                       // cannot be the main branch; K4 takes the exact path
+    if (tid == 0) { hdr->kth_key = 0; hdr->have_tentative = 0; hdr->ties = 0; }
+    return;
+  }
+  const u64* cand = p.cand + (size_t)b * p.H * p.W;
+  const u32* hist = p.chist + (size_t)b * HIST_BINS;
+  // thread t owns bins [4*(255-t) .. +3] so that thread order = descending score
+  const int top = HIST_BINS - 1 - 4 * tid;
+  u32 h[4], mine = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { h[i] = hist[top - i]; mine += h[i]; }
+  u32 incl = mine;
+#pragma unroll
+  for (int sft = 1; sft < 32; sft <<= 1) {
+    const u32 t = __shfl_up_sync(0xffffffffu, incl, sft);
+    if (lane >= sft) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  if (tid == 0) { counter = 0; eq_total = 0; }
+  __syncthreads();
+  u32 before = 0;
+  for (int w = 0; w < warp; ++w) before += wsum[w];
+  const u32 excl = before + incl - mine;                    // candidates in bins above this thread's
+  if ((u32)p.K > excl && (u32)p.K <= excl + mine) {         // exactly one thread
+    u32 c = excl;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (c + h[i] >= (u32)p.K) { cut_bin = (u32)(top - i); list_len = c + h[i]; break; }
+      c += h[i];
+    }
+  }
+  __syncthreads();
+  const int cut = (int)cut_bin;
+  const int L = (int)list_len;                               // K <= L
+  u64 kth;
+  if (L <= cap) {
+    int cap2 = 1;
+    while (cap2 < L) cap2 <<= 1;
+    for (int i = tid; i < cap2; i += TOPK2_THREADS) buf[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += TOPK2_THREADS) {
+      const u64 k = cand[i];
+      if (score_bin((u32)(k >> 32)) >= cut) buf[atomicAdd(&counter, 1u)] = k;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc(buf, cap2);
+    kth = buf[p.K - 1];
+    const u32 ksc = (u32)(kth >> 32);
+    u32 local = 0;
+    for (int i = p.K + tid; i < L; i += TOPK2_THREADS) local += ((u32)(buf[i] >> 32) == ksc) ? 1u : 0u;
+    local = warp_reduce_sum(local);
+    if (lane == 0 && local) atomicAdd(&eq_total, local);
+  } else {
+    // boundary bin holds more keys than the buffer (plateaus / quantised maps): exact select
+    CandSrc src{cand};
+    kth = block_topk_sorted(src, n, p.K, buf, cap >= 2 * p.K ? (cap >> 1) : cap, &ss_fallback, &counter);
+    const u32 ksc = (u32)(kth >> 32);
+    u32 local = 0;
+    for (int i = tid; i < n; i += TOPK2_THREADS) {
+      const u64 k = cand[i];
+      if ((u32)(k >> 32) == ksc && k < kth) ++local;
+    }
+    local = warp_reduce_sum(local);
+    if (lane == 0 && local) atomicAdd(&eq_total, local);
+  }
+  __syncthreads();
+  for (int i = tid; i < p.K; i += TOPK2_THREADS) {
+    const u64 k = buf[i];
+    write_row(p, b, i, key_index(k), __uint_as_float((u32)(k >> 32)));
+  }
+  if (tid == 0) { hdr->kth_key = kth; hdr->have_tentative = 1; hdr->ties = eq_total; }
+}
+
 // ------------------------------------------------------------------------------------------ K3
 __global__ void __launch_bounds__(256) decode_count_kernel(DecodeParams p, int chunks_per_img) {
   __shared__ u32 red[33];
@@ -456,6 +738,12 @@ __global__ void __launch_bounds__(256) decode_count_kernel(DecodeParams p, int c
   if (!hdr->have_tentative) return;
   const float kth = __uint_as_float((u32)(hdr->kth_key >> 32));
   const int n = p.H * p.W;
+  {
+    // the scan counted the pixels below hint[b]; when hint[b] <= kth that is a lower bound of what this
+    // kernel would count, and if it already exceeds the quantile's upper rank the map is not read again
+    const int hi = (int)ceilf(__fmul_rn(p.pct, (float)(n - 1)));
+    if (p.hint[b] <= kth && hdr->spec_below > (u32)hi) return;
+  }
   const size_t img = (size_t)b * n;
   int per = (n + chunks_per_img - 1) / chunks_per_img;
   per = (per + 3) & ~3;                                       // chunk boundaries stay 16-byte aligned
@@ -521,7 +809,7 @@ __device__ u32 block_count_band(const u64* keys, int n, float lo, float hi, u32*
   return block_reduce_sum(c, red);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) decode_resolve_kernel(DecodeParams p, int kpad) {
+__global__ void __launch_bounds__(RES_THREADS) decode_resolve_kernel(DecodeParams p, int kpad) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   u64* buf = reinterpret_cast<u64*>(smem_raw);
   SelectScratch* ss = reinterpret_cast<SelectScratch*>(buf + kpad);
@@ -541,7 +829,12 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_resolve_kernel(DecodeParam
     float rank = __fmul_rn(p.pct, (float)(npx - 1));
     int hi = (int)ceilf(rank);
     float kth = __uint_as_float((u32)(hdr->kth_key >> 32));
-    if (hdr->have_tentative && hdr->below_count > (u32)hi && kth > p.floor) {
+    const float hint = p.hint[b];
+    const bool have = hdr->have_tentative != 0;
+    const bool proven = hdr->below_count > (u32)hi || (hint <= kth && hdr->spec_below > (u32)hi);
+    __syncthreads();                                           // every thread has read the old hint
+    if (have && threadIdx.x == 0) p.hint[b] = 0.95f * kth;     // next call's speculative threshold
+    if (have && proven && kth > p.floor) {
       if (info && threadIdx.x == 0) {
         info[0] = 0; info[1] = -1; info[2] = (int32_t)hdr->ties; info[3] = ncand;
       }
@@ -628,6 +921,8 @@ __global__ void __launch_bounds__(SEL_THREADS) decode_resolve_kernel(DecodeParam
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 size_t hdr_bytes(int B) { return align_up((size_t)B * sizeof(ImgHeader), 256); }
+size_t hint_bytes(int B) { return align_up((size_t)B * sizeof(float), 256); }
+size_t hist_bytes(int B) { return align_up((size_t)B * HIST_BINS * sizeof(u32), 256); }
 
 }  // namespace
 }  // namespace sslam
@@ -637,7 +932,7 @@ using namespace sslam;
 extern "C" size_t sslam_decode_workspace_bytes(int B, int H, int W, int K) {
   (void)K;
   if (B <= 0 || H <= 0 || W <= 0) return 0;
-  return hdr_bytes(B) + (size_t)B * H * W * sizeof(u64);
+  return hdr_bytes(B) + hint_bytes(B) + hist_bytes(B) + (size_t)B * H * W * sizeof(u64);
 }
 
 extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, int H, int W, int K,
@@ -664,13 +959,41 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
   DecodeParams p;
   p.sal = sal; p.from_logits = from_logits; p.B = B; p.H = H; p.W = W; p.K = K; p.r = nms_radius;
   p.pct = pct; p.floor = floor; p.kpts = kpts_xy; p.scores = scores; p.info = info;
+  // workspace: [headers | hints (NOT cleared: they persist from call to call) | candidate histograms | keys]
   p.hdr = reinterpret_cast<ImgHeader*>(ws);
-  p.cand = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws) + hdr_bytes(B));
+  p.hint = reinterpret_cast<float*>(reinterpret_cast<char*>(ws) + hdr_bytes(B));
+  p.chist = reinterpret_cast<u32*>(reinterpret_cast<char*>(ws) + hdr_bytes(B) + hint_bytes(B));
+  p.cand = reinterpret_cast<u64*>(reinterpret_cast<char*>(ws) + hdr_bytes(B) + hint_bytes(B) + hist_bytes(B));
   SSLAM_CHECK_CUDA(cudaMemsetAsync(p.hdr, 0, (size_t)B * sizeof(ImgHeader), stream));
 
   const int r = nms_radius;
   const bool vec_ok = (W % 4 == 0) && (W >= 64) && ((reinterpret_cast<uintptr_t>(sal) & 15) == 0);
-  if (r >= 1 && r <= 3 && vec_ok) {
+  const int stream_strips = (W + 119) / 120;
+  const size_t stream_stage = (size_t)(2 * r + 1) * W * 4;
+  const bool stream_ok = r >= 1 && r <= 3 && vec_ok && stream_strips <= STREAM_MAX_WARPS && H >= 8 &&
+                         2 * stream_stage <= 88 * 1024 && !g_decode_no_stream;
+  bool hist_topk = false;
+  if (stream_ok) {
+    SSLAM_CHECK_CUDA(cudaMemsetAsync(p.chist, 0, (size_t)B * HIST_BINS * sizeof(u32), stream));
+    int NS = (int)((88 * 1024) / stream_stage);
+    if (NS > 16) NS = 16;
+    const int nbands = (H + 127) / 128;
+    const int band_rows = (H + nbands - 1) / nbands;
+    const size_t dyn = (size_t)NS * stream_stage;
+    static DeviceOnce once_stream;
+    if (once_stream.first_use()) {
+      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
+      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
+      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
+    }
+    const unsigned blocks = (unsigned)(B * nbands);
+    const unsigned threads = 32u * (unsigned)(stream_strips + 1);
+    SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
+                 if (r == 1) decode_scan_stream_kernel<1><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS);
+                 else if (r == 2) decode_scan_stream_kernel<2><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS);
+                 else decode_scan_stream_kernel<3><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS));
+    hist_topk = true;
+  } else if (r >= 1 && r <= 3 && vec_ok) {
     const int nstrips = (W + 119) / 120;                       // 120 output columns per warp
     int nseg = (H + 63) / 64;                                  // ~64 rows per warp
     const int seg_rows = (H + nseg - 1) / nseg;
@@ -706,15 +1029,26 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
     SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_resolve_kernel,
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   }
-  SSLAM_LAUNCH(KK_DECODE_TOPK, stream,
-               decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));
+  if (hist_topk) {
+    const int cap = 2 * kpad;                                  // K + boundary bin; pow2
+    const size_t smem2 = (size_t)cap * 8;
+    static DeviceOnce once2;
+    if (once2.first_use())
+      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_topk_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            200 * 1024));
+    SSLAM_LAUNCH(KK_DECODE_TOPK, stream,
+                 decode_topk_hist_kernel<<<B, TOPK2_THREADS, smem2, stream>>>(p, cap));
+  } else {
+    SSLAM_LAUNCH(KK_DECODE_TOPK, stream,
+                 decode_topk_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));
+  }
 
   int chunks = (H * W + 16383) / 16384;
   if (chunks < 1) chunks = 1;
   SSLAM_LAUNCH(KK_DECODE_COUNT, stream,
                decode_count_kernel<<<B * chunks, 256, 0, stream>>>(p, chunks));
   SSLAM_LAUNCH(KK_DECODE_RESOLVE, stream,
-               decode_resolve_kernel<<<B, SEL_THREADS, sel_smem, stream>>>(p, kpad));
+               decode_resolve_kernel<<<B, RES_THREADS, sel_smem, stream>>>(p, kpad));
   return SSLAM_OK;
 }
 
@@ -740,3 +1074,7 @@ extern "C" int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radi
                nms_kernel<<<g, SCAN_THREADS, smem, stream>>>(sal, H, W, r, out));
   return SSLAM_OK;
 }
+
+// Debug aid for tests / tools (include/sslam_b200_debug.h): 0 forces the register-prefetching scan
+// kernels + radix-select top-k instead of the shared-memory streaming scan + histogram top-k.
+extern "C" void sslam_debug_decode_stream(int on) { sslam::g_decode_no_stream = (on == 0); }

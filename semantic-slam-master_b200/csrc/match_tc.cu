@@ -681,6 +681,7 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
       g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   });
   SSLAM_REQUIRE(g_encode != nullptr, SSLAM_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (swizzle_bytes < 0) return SSLAM_OK;                      // entry-point resolution only
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {cols * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_cols, box_rows};
@@ -693,6 +694,24 @@ int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SSLAM_REQUIRE(r == CUDA_SUCCESS, SSLAM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return SSLAM_OK;
+}
+// NHWC tensor [B,H,W,C] (2-byte elements) as a 4-D map with a {box_c, box_w, box_h, 1} box and
+// 128-byte swizzle: box_c * 2 bytes = 128, so a box lands in shared memory as box_h*box_w rows of 128
+// bytes — the K-major SWIZZLE_128B operand tile whose rows are the pixels of a (box_h x box_w) window.
+// Coordinates may be negative / beyond the image: those elements are zero-filled (convolution padding).
+int make_tensor_map_nhwc(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                         uint32_t box_h, uint32_t box_w, uint32_t box_c) {
+  int rc = make_tensor_map_2d(nullptr, nullptr, 0, 0, 0, 0, 0, -1);      // resolves the driver entry point only
+  if (rc) return rc;
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SSLAM_REQUIRE(r == CUDA_SUCCESS, SSLAM_ECUDA, "cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
   return SSLAM_OK;
 }
 }  // namespace tc

@@ -20,6 +20,11 @@ namespace tc {
 int make_tensor_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols,
                        uint32_t box_rows, uint32_t box_cols, int elem_bytes, int swizzle_bytes = 128);
 
+// NHWC [B,H,W,C] tensor of 2-byte elements as a 4-D map, box {box_c, box_w, box_h, 1}, 128-byte swizzle
+// (box_c * 2 == 128); out-of-range coordinates are zero-filled.
+int make_tensor_map_nhwc(CUtensorMap* map, const void* base, uint64_t B, uint64_t H, uint64_t W, uint64_t C,
+                         uint32_t box_h, uint32_t box_w, uint32_t box_c);
+
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------ device side
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -110,6 +115,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// 4-D tile load (NHWC maps): coordinates (c, x, y, b), signed — out-of-range parts are zero-filled
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 

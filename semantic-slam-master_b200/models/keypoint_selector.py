@@ -4,7 +4,8 @@ Same surface as the reference class (models/keypoint_selector.py:15-226 there): 
 arguments, ``state_dict`` keys (``conv.0.*``, ``conv.2.*``), ``forward``, ``select_keypoints`` and
 ``_apply_nms`` keep their names, keywords, defaults, shapes and dtypes, so a reference checkpoint
 loads unchanged and callers need no edits.  The saliency head (3x3 conv -> ReLU -> 1x1 conv ->
-sigmoid) stays PyTorch; ``select_keypoints`` — percentile threshold, NMS, candidate compaction,
+sigmoid) is one tcgen05 implicit-GEMM kernel under ``torch.no_grad()`` (``sslam_selector_head_f32``;
+PyTorch layers when autograd is recording); ``select_keypoints`` — percentile threshold, NMS, candidate compaction,
 top-k and the fallback branches — is one batched, sync-free call into ``sslam_decode_topk_f32``.
 """
 
@@ -27,10 +28,32 @@ class KeypointSelector(nn.Module):
             nn.init.xavier_uniform_(layer.weight, gain=0.5)
             nn.init.constant_(layer.bias, 0.0)
 
-    def forward(self, dino_features: torch.Tensor) -> torch.Tensor:
-        """(B, H, W, C) patch features -> (B, H, W, 1) sigmoid saliency."""
+    head = "tcgen05"         # "tcgen05" (default) or "torch" (cuDNN convolutions, for A/B comparisons)
+
+    def _plan(self):
+        ps = [self.conv[0].weight, self.conv[0].bias, self.conv[2].weight, self.conv[2].bias]
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        if getattr(self, "_plan_key", None) != key:
+            self._plan_obj = ops.SelectorPlan(*ps)
+            self._plan_key = key
+        return self._plan_obj
+
+    def _kernel_ok(self, x):
+        c0, c2 = self.conv[0], self.conv[2]
+        return (self.head == "tcgen05" and x.is_cuda and x.dtype == torch.float32
+                and c0.in_channels % 64 == 0 and c0.out_channels % 8 == 0 and c0.out_channels <= 512
+                and c2.out_channels == 1)
+
+    def forward(self, dino_features: torch.Tensor, return_logits: bool = False) -> torch.Tensor:
+        """(B, H, W, C) patch features -> (B, H, W, 1) sigmoid saliency.  Without autograd on a CUDA
+        device the whole head (3x3 conv, ReLU, 1x1 conv, sigmoid) is one tcgen05 implicit-GEMM kernel
+        (sslam_selector_head_f32); when gradients are needed the PyTorch layers run."""
+        grad = torch.is_grad_enabled() and (dino_features.requires_grad or
+                                            any(p.requires_grad for p in self.parameters()))
+        if not grad and self._kernel_ok(dino_features):
+            return ops.selector_head(self._plan(), dino_features, apply_sigmoid=not return_logits).unsqueeze(-1)
         logits = self.conv(dino_features.permute(0, 3, 1, 2))
-        return torch.sigmoid(logits).permute(0, 2, 3, 1)
+        return (logits if return_logits else torch.sigmoid(logits)).permute(0, 2, 3, 1)
 
     def select_keypoints(self, saliency_map: torch.Tensor, num_keypoints: int = 500,
                          nms_radius: int = 2, min_score_percentile: float = 0.50

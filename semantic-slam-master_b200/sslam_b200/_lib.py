@@ -49,6 +49,11 @@ SIGNATURES = {
                                  c_void_p]),
     "sslam_eval_matches": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                    c_void_p, c_void_p, c_void_p]),
+    "sslam_selector_packed_bytes": (c_size_t, [c_int, c_int]),
+    "sslam_selector_pack_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "sslam_selector_workspace_bytes": (c_size_t, [c_int] * 4),
+    "sslam_selector_head_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sslam_heatmap_from_cells_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
@@ -57,6 +62,7 @@ DEBUG_SIGNATURES = {
     "sslam_debug_match_stalls": (None, [c_void_p]),
     "sslam_debug_gemm_stalls": (None, [c_void_p]),
     "sslam_debug_watchdog_gemm": (c_int, [c_void_p]),
+    "sslam_debug_decode_stream": (None, [c_int]),
 }
 
 ERROR_NAMES = {-1: "SSLAM_EINVAL", -2: "SSLAM_EUNSUPPORTED", -3: "SSLAM_EWORKSPACE",

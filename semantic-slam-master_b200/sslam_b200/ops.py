@@ -370,3 +370,44 @@ def heatmap_from_cells(logits, cell=8, border=0):
     heat = torch.empty(B, Hc * cell, Wc * cell, dtype=torch.float32, device=x.device)
     _lib.check(lib.sslam_heatmap_from_cells_f32(_ptr(x), B, Hc, Wc, int(cell), int(border), _ptr(heat), _stream()))
     return heat
+
+
+# ---------------------------------------------------------------------------------- selector head (N2)
+class SelectorPlan:
+    """Packed fp16 (hi, lo) weights of the selector's 3x3 convolution, reordered to [hidden][tap][C]."""
+
+    def __init__(self, conv1_weight, conv1_bias, conv2_weight, conv2_bias):
+        lib = _lib.load()
+        _need_cuda(conv1_weight, conv1_bias, conv2_weight, conv2_bias)
+        w1 = conv1_weight.detach().contiguous()
+        if w1.dtype != torch.float32 or w1.dim() != 4 or tuple(w1.shape[2:]) != (3, 3):
+            raise RuntimeError("selector head expects an fp32 [hidden, C, 3, 3] convolution weight")
+        self.hidden, self.C = int(w1.shape[0]), int(w1.shape[1])
+        self.b1 = conv1_bias.detach().contiguous()
+        self.w2 = conv2_weight.detach().reshape(-1).contiguous()
+        self.b2 = conv2_bias.detach().reshape(-1).contiguous()
+        if self.w2.numel() != self.hidden or self.b2.numel() != 1:
+            raise RuntimeError("selector head expects a [1, hidden, 1, 1] second convolution")
+        nbytes = lib.sslam_selector_packed_bytes(self.C, self.hidden)
+        self.packed = torch.empty(nbytes, dtype=torch.uint8, device=w1.device)
+        _lib.check(lib.sslam_selector_pack_weights(_ptr(w1), self.C, self.hidden, _ptr(self.packed), nbytes,
+                                                   _stream()))
+
+
+def selector_head(plan, features, apply_sigmoid=True, out=None, workspace=None):
+    """features (B,H,W,C) fp32 NHWC -> (B,H,W) fp32 saliency (or logits): 3x3 conv + ReLU + 1x1 conv
+    [+ sigmoid] as one tcgen05 implicit-GEMM kernel."""
+    lib = _lib.load()
+    _need_cuda(features)
+    f = features.contiguous()
+    if f.dtype != torch.float32 or f.dim() != 4 or f.shape[-1] != plan.C:
+        raise RuntimeError("selector_head expects fp32 (B,H,W,%d) features" % plan.C)
+    B, H, W, C = f.shape
+    if out is None:
+        out = torch.empty(B, H, W, dtype=torch.float32, device=f.device)
+    need = lib.sslam_selector_workspace_bytes(B, H, W, C)
+    ws = workspace if workspace is not None else _ws("selector", need, f.device)
+    _lib.check(lib.sslam_selector_head_f32(_ptr(f), _ptr(plan.packed), _ptr(plan.b1), _ptr(plan.w2), _ptr(plan.b2),
+                                           B, H, W, C, plan.hidden, 1 if apply_sigmoid else 0, _ptr(out), _ptr(ws),
+                                           ws.numel(), _stream()))
+    return out

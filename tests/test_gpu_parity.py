@@ -34,8 +34,18 @@ def cu(x, dev):
 
 
 # ------------------------------------------------------------------------------------ decode
+@pytest.fixture(params=["stream", "register"])
+def scan_path(request):
+    """Run a decode test with the streaming scan + histogram top-k (default where eligible) and again
+    with the register-prefetching scan + radix-select top-k forced (the fallback kernels)."""
+    from sslam_b200 import _lib
+    _lib.load().sslam_debug_decode_stream(1 if request.param == "stream" else 0)
+    yield request.param
+    _lib.load().sslam_debug_decode_stream(1)
+
+
 @pytest.mark.parametrize("name", DEC_CASES)
-def test_decode_golden(name, dev):
+def test_decode_golden(name, dev, scan_path):
     from sslam_b200 import ops
     sal, m = decode_case_input(name)
     kp, sc, info = ops.decode_topk(cu(sal[None], dev), m["K"], m["nms_radius"], m["pct"])
@@ -53,7 +63,7 @@ def test_decode_golden(name, dev):
     assert np.array_equal(okp[0], kp) and np.array_equal(osc[0], sc)
 
 
-def test_decode_mixed_batch(dev):
+def test_decode_mixed_batch(dev, scan_path):
     """Several maps of one size in a single call take different branches independently."""
     from sslam_b200 import ops
     maps = [recipes.spread_saliency(48, 64, 101), np.full((48, 64), 0.05, np.float32),
@@ -110,7 +120,32 @@ def test_nms_golden(dev):
         assert np.array_equal(out.cpu().numpy()[0], DEC[f"nms.r{r}"])
 
 
-def test_decode_full_size_properties(dev):
+def test_decode_speculative_count_is_only_a_hint(dev):
+    """The scan counts pixels below a per-slot hint left by the previous call (0.95 x that slot's last
+    K-th score) so that the second pass over the map can be skipped.  Whatever the hint holds — nothing
+    (first call), a good value (same data again), a value far too high or too low (different data in the
+    same workspace slot) — keypoints, scores and the branch taken must equal the oracle's."""
+    from sslam_b200 import ops
+    H, W, K = 96, 256, 64
+    ws = ops.Workspace()
+    lib_need = ops._lib.load().sslam_decode_workspace_bytes(3, H, W, K)
+    buf = ws.get(lib_need, dev)
+    buf.zero_()
+    hi = np.stack([recipes.spread_saliency(H, W, 301 + i, lo=0.6, hi=0.99) for i in range(3)])
+    lo = np.stack([recipes.spread_saliency(H, W, 311 + i, lo=0.02, hi=0.3) for i in range(3)])
+    mid = np.stack([recipes.box_saliency(H, W, 321 + i) for i in range(3)])
+    for maps in (hi, hi, lo, lo, mid, hi, mid, mid):
+        kp, sc, info = ops.decode_topk(cu(maps, dev), K, workspace=buf)
+        okp, osc, oinfo = oracle.select_keypoints(maps, K)
+        assert np.array_equal(info.cpu().numpy()[:, 0], oinfo[:, 0])
+        assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
+    buf.fill_(0xff)                                              # garbage (NaN) hints
+    kp, sc, info = ops.decode_topk(cu(mid, dev), K, workspace=buf)
+    okp, osc, oinfo = oracle.select_keypoints(mid, K)
+    assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
+
+
+def test_decode_full_size_properties(dev, scan_path):
     """BASELINE sizes (640x480 K=2048, 1280x960 K=8192) on the seeded synthetic sequence:
     identical to the oracle, plus size-independent properties."""
     from sslam_b200 import ops, synth
@@ -439,7 +474,7 @@ def test_empty_and_degenerate_shapes(dev):
         ops.match_top2(torch.rand(1, 4, 12, device=dev), torch.rand(1, 4, 12, device=dev))   # f16x3 default: D % 8
 
 
-def test_decode_all_radii_and_percentiles(dev):
+def test_decode_all_radii_and_percentiles(dev, scan_path):
     """Strip kernel (radius 1..3) and tiled kernel (radius 0, 4..8) against the oracle."""
     from sslam_b200 import ops
     sal = np.stack([recipes.spread_saliency(70, 150, 200 + i) for i in range(3)] +

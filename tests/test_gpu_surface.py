@@ -293,3 +293,87 @@ def test_cell_softmax_decode_mode(dev):
         assert torch.equal(h2, heat)
         okp, osc, _ = oracle.select_keypoints(heat.cpu().numpy(), K)
         assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
+
+
+def test_selector_head_kernel(dev):
+    """the selector head (3x3 conv -> ReLU -> 1x1 conv -> sigmoid) as one tcgen05
+    implicit-GEMM kernel.  Logits within 1e-5 x max(1, max|logit|) of the fp32 PyTorch head (cuDNN with
+    TF32 off, and the CPU head) and of an fp64 evaluation, on the reference-native 28x28 grid, the 30x40
+    and 60x80 grids and ragged shapes.  The weights here are inflated (1x1 weights x4, non-zero biases) so
+    that logits reach |4|; the tolerance is stated relative to that scale (K = 9*384 = 3456 products per
+    hidden unit; the error of the fp32 PyTorch heads against fp64 is recorded beside ours).  The
+    reference-initialised head is held to an absolute 1e-5 by test_selector_head_c0_fixture."""
+    from models.keypoint_selector import KeypointSelector
+    from sslam_b200 import ops
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(31)
+        for (B, H, W, hidden) in ((2, 28, 28, 256), (3, 30, 40, 128), (1, 60, 80, 256), (2, 5, 7, 136), (1, 1, 1, 8),
+                                  (1, 33, 130, 64)):
+            torch.manual_seed(hidden)
+            sel = KeypointSelector(384, hidden).to(dev).eval()
+            with torch.no_grad():
+                sel.conv[0].bias.uniform_(-0.2, 0.2)             # the reference initialises biases to 0
+                sel.conv[2].bias.fill_(0.3)
+                sel.conv[2].weight.mul_(4.0)
+            feat = torch.randn(B, H, W, 384, generator=g).to(dev)
+            ops.profile_enable(True)
+            with torch.no_grad():
+                sal = sel(feat)
+                logit = sel(feat, return_logits=True)
+            torch.cuda.synchronize()
+            kinds = ops.profile_read()
+            ops.profile_enable(False)
+            assert kinds.get("conv_head", (0, 0))[1] == 2, kinds
+            assert sal.shape == (B, H, W, 1) and sal.dtype == torch.float32
+            sel.head = "torch"
+            with torch.no_grad():
+                ref_logit = sel(feat, return_logits=True)
+            sel.head = "tcgen05"
+            cpu = KeypointSelector(384, hidden).eval()
+            cpu.load_state_dict(sel.state_dict())
+            with torch.no_grad():
+                cpu_logit = cpu.conv(feat.cpu().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+                f64_logit = cpu.double().conv(feat.cpu().double().permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+            e_gpu = float((logit - ref_logit).abs().max())
+            e_cpu = float((logit.cpu() - cpu_logit).abs().max())
+            e_f64 = float((logit.cpu().double() - f64_logit).abs().max())
+            scale = max(1.0, float(ref_logit.abs().max()))
+            record(f"selector_head.{B}x{H}x{W}x{hidden}", {"max_abs_logit_err_vs_cudnn_fp32": e_gpu,
+                                                           "max_abs_logit_err_vs_cpu": e_cpu,
+                                                           "max_abs_logit_err_vs_fp64": e_f64,
+                                                           "cudnn_fp32_err_vs_fp64": float((ref_logit.cpu().double() - f64_logit).abs().max()),
+                                                           "cpu_fp32_err_vs_fp64": float((cpu_logit.double() - f64_logit).abs().max()),
+                                                           "logit_abs_max": float(ref_logit.abs().max())})
+            tol = 1e-5 * scale
+            assert e_gpu < tol and e_cpu < tol and e_f64 < tol, (e_gpu, e_cpu, e_f64, tol)
+            assert torch.allclose(sal, torch.sigmoid(ref_logit), rtol=0, atol=1e-5)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+
+
+def test_selector_head_c0_fixture(dev):
+    """c0 end to end without a library kernel: seeded selector weights + seeded 28x28 features ->
+    saliency within 1e-5 of the reference's (tests/golden/decode.npz: c0.sal, written by the
+    reference's own KeypointSelector on CPU) and the same 500 keypoints (branch B, duplicates)."""
+    from models.keypoint_selector import KeypointSelector
+    from test_oracle_golden import DEC
+    torch.manual_seed(0)
+    sel = KeypointSelector(384, 256).to(dev).eval()
+    g = torch.Generator().manual_seed(7)
+    feats = torch.randn(2, 28, 28, 384, generator=g).to(dev)
+    with torch.no_grad():
+        sal = sel(feats)
+        kp, sc = sel.select_keypoints(sal, num_keypoints=500)
+    err = np.abs(sal[..., 0].cpu().numpy() - DEC["c0.sal"]).max()
+    assert err < 1e-5, err
+    same = np.array_equal(kp.cpu().numpy(), DEC["c0.kpts"])
+    record("selector_head.c0", {"max_abs_saliency_err": float(err), "keypoints_identical": bool(same)})
+    assert np.allclose(sc.cpu().numpy(), DEC["c0.scores"], rtol=0, atol=1e-5)
+    if not same:
+        # a keypoint may only move where two saliency values are closer than the head's arithmetic error
+        okp, osc, _ = oracle.select_keypoints(DEC["c0.sal"], 500)
+        diff = np.nonzero((kp.cpu().numpy() != okp).any(-1))
+        assert np.abs(sc.cpu().numpy()[diff] - osc[diff]).max() < 2e-5
+        assert len(diff[0]) < 10
