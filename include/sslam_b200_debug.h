@@ -25,6 +25,10 @@ int sslam_debug_watchdog_gemm(unsigned long long* buf);
  * streaming scan does not take); non-zero (default): streaming scan + histogram top-k where eligible. */
 void sslam_debug_decode_stream(int on);
 
+/* DescriptorRefiner forward: 0 = one GEMM launch per layer; 1..4 = the layer-fused persistent kernel with
+ * that many 256-row strip pairs per chunk (default 3).  Both paths compute bit-identical results. */
+void sslam_debug_refiner_fused(int mode);
+
 #ifdef __cplusplus
 }
 #endif

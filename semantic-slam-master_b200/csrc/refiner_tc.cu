@@ -39,6 +39,7 @@ namespace sslam {
 using namespace tc;
 
 long long* g_gemm_dbg = nullptr;    // set by sslam_debug_gemm_stalls (tools only, not part of the ABI)
+int g_refiner_fused = 3;            // 0: one launch per layer; 1..4: layer-fused kernel, strip pairs per chunk (sslam_debug_refiner_fused)
 
 namespace {
 
@@ -551,14 +552,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const __half* res_h = RES ? p.res_hi + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
       const __half* res_l = RES ? p.res_lo + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
       auto load_res = [&](int gc, uint4 (&h)[2], uint4 (&l)[2]) {
-        if (gc + UNIT <= p.N) {                         // one 32-byte sector per array: 256-bit loads
-          ldg_256(res_h + gc, h);
+        if (gc + UNIT <= p.N && (p.N & 15) == 0) {      // one 32-byte sector per array: 256-bit loads
+          ldg_256(res_h + gc, h);                       // (rows are 32-byte aligned only when N % 16 == 0)
           ldg_256(res_l + gc, l);
         } else {
           h[0] = h[1] = l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
           if (gc < p.N) {
             h[0] = __ldg(reinterpret_cast<const uint4*>(res_h + gc));
             l[0] = __ldg(reinterpret_cast<const uint4*>(res_l + gc));
+          }
+          if (gc + 8 < p.N) {
+            h[1] = __ldg(reinterpret_cast<const uint4*>(res_h + gc + 8));
+            l[1] = __ldg(reinterpret_cast<const uint4*>(res_l + gc + 8));
           }
         }
       };
@@ -697,6 +702,662 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Layer-fused forward: ONE persistent launch runs input projection -> [fc1, fc2 + identity] x blocks
+// -> output projection for every row; the activations between layers never reach HBM.
+//
+// The per-layer kernel above round-trips a [rows, hidden] fp16 pair through HBM for every layer
+// (ncu: 12.8 GB per 300 c2 frames against 2.2 GB of input + output), which holds the tensor pipe at
+// 40-75 %.  A 128-row strip's activation pair (192 KB) plus the next layer's does not fit in one SM's
+// shared memory or TMEM, so the exchange medium is the 126 MB L2 instead:
+//   * same cluster shape and data path as gemm_pair_kernel: `ntile` CTA pairs (cta_group::2, M = 256),
+//     pair ct owns output columns [128 ct, 128 ct + 128) of EVERY layer; activation k-blocks are TMA-
+//     multicast to the pairs; the epilogue threads store their rows of the fp16 pair straight from
+//     registers (32-byte sectors).
+//   * a cluster works on chunks of S strip pairs (S x 256 rows).  Order inside a chunk: layer-major,
+//     strip-minor (l0: s0..sS-1, l1: s0..sS-1, ...).  The layer outputs go to a per-cluster scratch
+//     (h and u pairs, S x 256 rows each: groups x S x 768 KB = ~50 MB for 22 clusters and S = 3) that
+//     is rewritten every chunk and therefore stays dirty in L2: after the input rows have been read
+//     once, nothing but the final descriptors is written back to DRAM.  fc2 + identity updates h in
+//     place (the thread that adds the residual element is the one that stores it).
+//   * strip s of layer l+1 may be loaded once all 2*ntile CTAs have stored their columns of strip s of
+//     layer l: each epilogue warp, half a tile after its last store, issues a release fence and
+//     arrives on the `ready[s]` mbarrier of every CTA of the cluster; the producers wait on it, acquire
+//     and order their TMA loads behind it (fence.proxy.async).  With S >= 3 the wait has more than a
+//     tile of slack and never stalls the tensor pipe.
+//   * weights are layer-stationary instead of launch-stationary: a dedicated warp reloads the pair's
+//     128 weight columns k-block by k-block behind the last strip of the previous layer (`wfree[kb]`
+//     is committed by that strip's MMAs, `wfull[kb]` gates the first strip of the next layer), so the
+//     switch costs no bubble; 96 KB per CTA and layer out of L2, amortised over S strips.
+//   * arithmetic, k order and epilogue are those of gemm_pair_kernel: results are bit-identical to the
+//     per-layer path (tests/test_gpu_tc.py).
+// Row statistics for the folded LayerNorms and the residual are read back with ld.global.cg: the
+// buffers are rewritten inside this launch, so the non-coherent path (ld.global.nc / L1) must not be used.
+constexpr int F_MAX_LAYERS = 8;                           // 2 + 2 * blocks, blocks <= 3
+constexpr int F_MAX_SLOTS = 4;                            // strip pairs per chunk (S)
+constexpr int F_THREADS = NUM_THREADS + 64;               // + the weight producer warp and the publisher warp
+constexpr int F_W_WARP = NUM_THREADS / 32;
+constexpr int F_PUB_WARP = F_W_WARP + 1;
+// Activation stages: F_BK K-elements of the CTA's 128 rows, hi and lo.  Measured on c2 (300 frames, S = 3):
+//   3 x 32 KB (F_BK 64, SWIZZLE_128B)  3.4 - 3.6 ms      7 x 16 KB (F_BK 32, SWIZZLE_64B)  3.9 - 4.1 ms
+//   4 x 32 KB (all of shared memory, bias vectors read through L1 instead)  5.0 ms
+// i.e. the feed is not short of bytes in flight: both the per-layer kernel and this one settle at about
+// 192 KB of A operand per 8.5 - 9k cycles and SM (~22 B/clk).
+constexpr int F_BK = 64;
+constexpr int F_HALF_BYTES = BM * F_BK * 2;               // one 128-row operand tile of a stage
+constexpr int F_STAGE_BYTES = 2 * F_HALF_BYTES;           // A_hi, A_lo
+constexpr int F_STAGES = F_BK == 64 ? 3 : 7;
+constexpr int F_SUB = BK / F_BK;                          // stages per 64-element weight k-block
+constexpr int F_SMEM_A = F_STAGES * F_STAGE_BYTES;
+constexpr int F_SMEM_VECS = F_MAX_LAYERS * 2 * BN * 4;    // [layer][bias 128 | s1 128] of the pair's columns
+constexpr int F_SMEM_LN = 2 * BM * 2 * 4;                 // [tile parity][row][-mean, rstd] of the tile's A operand
+constexpr int F_NBARS = 2 * F_STAGES + 2 * P_MAX_KB + 4 + F_MAX_SLOTS + 4 + 2;
+constexpr int F_SMEM_BARS = F_NBARS * 8 + 16;
+constexpr int F_SMEM_TOTAL = P_SMEM_B + F_SMEM_A + F_SMEM_VECS + F_SMEM_LN + F_SMEM_BARS + 1024;
+static_assert(F_SMEM_TOTAL <= 227 * 1024, "fused refiner kernel exceeds the shared memory of an SM");
+
+struct FusedMaps {
+  CUtensorMap a_hi[3], a_lo[3];      // operand loads: 0 = x (true rows), 1 = h, 2 = u (scratch rows)
+  CUtensorMap w_hi[F_MAX_LAYERS], w_lo[F_MAX_LAYERS];
+};
+
+struct FusedParams {
+  int rows, C, Hd, D, L, S, groups, ntile;
+  const float* bias[F_MAX_LAYERS];   // bias, or c0 of a LayerNorm-fed layer
+  const float* s1[F_MAX_LAYERS];     // null unless LayerNorm-fed
+  __half* s_hi[2];                   // scratch pairs [groups*S*256, Hd]: 0 = h (also the residual), 1 = u
+  __half* s_lo[2];
+  float* raw;                        // [rows, D] output of the last layer
+  float* st_sum[2];                  // partial row sums [2 * ntile][stat_stride]: 0 = of h, 1 = of u
+  float* st_sq[2];
+  size_t stat_stride;                // = groups * S * 256 scratch rows
+  long long* dbg;                    // optional per-CTA cycle counters (16 int64 per CTA), or null
+  int dbg_flags;
+};
+
+struct LayerInfo {
+  int K, N, src, dst, st_in, st_out;
+  bool ln, res, relu, f32, stats;
+};
+__device__ __forceinline__ LayerInfo layer_info(const FusedParams& p, int l) {
+  LayerInfo li;
+  const bool first = l == 0, last = l == p.L - 1;
+  const bool fc1 = !first && !last && (l & 1), fc2 = !first && !last && !(l & 1);
+  li.K = first ? p.C : p.Hd;
+  li.N = last ? p.D : p.Hd;
+  li.src = first ? 0 : (fc2 ? 2 : 1);
+  li.dst = fc1 ? 1 : 0;
+  li.st_in = fc2 ? 1 : 0;
+  li.st_out = fc1 ? 1 : 0;
+  li.ln = fc1 || fc2; li.res = fc2; li.relu = !last; li.f32 = last;
+  li.stats = first ? (p.L > 2) : (fc1 || (fc2 && l != p.L - 2));
+  return li;
+}
+
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void ld_cg_256(const void* ptr, uint4 (&d)[2]) {
+  asm volatile("ld.global.cg.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(d[0].x), "=r"(d[0].y), "=r"(d[0].z), "=r"(d[0].w), "=r"(d[1].x), "=r"(d[1].y), "=r"(d[1].z),
+                 "=r"(d[1].w)
+               : "l"(ptr));
+}
+__device__ __forceinline__ uint4 ld_cg_128(const void* ptr) {
+  uint4 d;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(ptr));
+  return d;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// what one epilogue warp needs for one tile
+struct EpiTile {
+  uint32_t tmem_base;
+  int q, half, lane, ct, col_base;
+  int N, K;                          // layer's output width / LayerNorm width
+  size_t srow;                       // this thread's scratch row (statistics, residual)
+  size_t orow;                       // this thread's row in the output array (scratch row, or true row for the last layer)
+  bool row_ok;                       // last layer: orow < rows
+  const float* sbias;                // this layer's 128 bias / c0 values of the pair's columns (shared memory)
+  const float* ss1;
+  __half* o_hi;                      // output pair (scratch h or u)
+  __half* o_lo;
+  float* o_f32;                      // raw output of the last layer
+  const __half* res_h;               // residual pair (scratch h)
+  const __half* res_l;
+  const float2* ln;                  // (-mean, rstd) of the CTA's 128 rows of the A operand (shared memory)
+  uint64_t* lnfull;                  // ... complete when this barrier's phase `ln_parity` is
+  uint32_t ln_parity;
+  float* out_sum;                    // partial row sums of the output, [2 * ntile][stat_stride]
+  float* out_sq;
+  size_t stat_stride;
+  long long* dbg_wait;               // debug: per-section cycle counters (null = off)
+  uint64_t* tfull;
+  uint32_t tempty_leader;
+};
+
+__device__ __forceinline__ void st_global_256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
+// Epilogue of one tile for one warp (32 rows x 64 columns, thread = row, 16 columns per unit).
+//
+// ONE body for every layer type (the kernel runs all of them, and five unrolled template instances were
+// 250 KB of code that the warps of an SM kept evicting from the 32 KB instruction cache): the layer's
+// options are data, not code —
+//   plain bias      = folded LayerNorm with rho = 1, mu = 0:  fma(1, fma(-0, s1, acc), bias) == acc + bias
+//   no ReLU         = max(x, -inf)
+//   row statistics  = always accumulated (2 instructions per element), stored only when wanted
+// and only the residual loads and the output format are (warp-uniform) branches.
+// Outputs leave the registers directly: a thread's 16 values of a unit are 32 contiguous, 32-byte
+// aligned bytes of its row in each array of the pair (one full sector: what a TMA box of the same shape
+// writes too), so there is no shared-memory staging, no proxy fence and no store queue to wait for
+// inside the tile.  Row sums are written per 64-column half (the consumer adds the halves of a column
+// tile first, then the tiles: the order of gemm_pair_kernel, bit-identical results).
+struct EpiFlags { bool ln, res, relu, f32, stats; };
+
+__device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiFlags fl, int acc, uint32_t tfull_parity) {
+  const int lane = c.lane, q = c.q, half = c.half;
+  long long* const dw = c.dbg_wait;
+  long long t0 = 0;
+#ifdef SSLAM_FUSED_SECTIONS                                // build-time switch of tools/fused_probe.py's section timers
+#define SEC(i) do { if (dw) { const long long t1_ = clock64(); dw[i] += t1_ - t0; t0 = t1_; } } while (0)
+  if (dw) t0 = clock64();
+#else
+#define SEC(i) do { } while (0)
+  (void)dw; (void)t0;
+#endif
+  const float lo_clamp = fl.relu ? 0.f : __int_as_float(0xff800000);
+  float rsum = 0.f, rsq = 0.f;
+  const __half* res_h = c.res_h + c.srow * (size_t)c.N;
+  const __half* res_l = c.res_l + c.srow * (size_t)c.N;
+  const bool wide = (c.N & 15) == 0;                     // rows are 32-byte aligned only when N % 16 == 0
+  uint4 nh[2], nl[2];
+  nh[0] = nh[1] = nl[0] = nl[1] = make_uint4(0u, 0u, 0u, 0u);
+  auto load_res = [&](int gc) {
+    if (gc + UNIT <= c.N && wide) {
+      ld_cg_256(res_h + gc, nh);
+      ld_cg_256(res_l + gc, nl);
+    } else {
+      nh[0] = nh[1] = nl[0] = nl[1] = make_uint4(0u, 0u, 0u, 0u);
+      if (gc < c.N) { nh[0] = ld_cg_128(res_h + gc); nl[0] = ld_cg_128(res_l + gc); }
+      if (gc + 8 < c.N) { nh[1] = ld_cg_128(res_h + gc + 8); nl[1] = ld_cg_128(res_l + gc + 8); }
+    }
+  };
+  if (fl.res) load_res(c.col_base + half * 64);          // in flight while the accumulator completes
+  SEC(1);
+  mbar_wait(&c.tfull[acc], tfull_parity);
+  SEC(0);
+  tcgen05_fence_after();
+  // (-mean, rstd) of this row of the A operand, from the publisher / LayerNorm warp (normally complete a
+  // tile ago; never read before lnfull — this warp may get here while other CTAs are still storing the
+  // statistics of the strip's previous layer)
+  float ar = 1.f, nam = -0.f;
+  if (fl.ln) {
+    mbar_wait(c.lnfull, c.ln_parity);
+    const float2 ln = c.ln[q * 32 + lane];
+    nam = ln.x; ar = ln.y;
+  }
+  uint32_t r[UNIT], rs[UNIT];
+  const uint32_t tbase = c.tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + half * 64;
+  tmem_ld_32x16(tbase, r);
+  tmem_ld_32x16(tbase + BN, rs);
+#pragma unroll
+  for (int un = 0; un < 64 / UNIT; ++un) {
+    const int col0 = half * 64 + un * UNIT;
+    const int gc0 = c.col_base + col0;
+    uint4 rh[2] = {nh[0], nh[1]}, rl[2] = {nl[0], nl[1]};
+    if (fl.res && un + 1 < 64 / UNIT) load_res(gc0 + UNIT);
+    float v[UNIT];
+    SEC(3);
+    tmem_ld_wait();
+    SEC(2);
+#pragma unroll
+    for (int j = 0; j < UNIT; ++j)
+      v[j] = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));     // fold the cross terms
+    if (un + 1 < 64 / UNIT) {                            // next unit's accumulators: in flight during the math
+      tmem_ld_32x16(tbase + (un + 1) * UNIT, r);
+      tmem_ld_32x16(tbase + (un + 1) * UNIT + BN, rs);
+    }
+    SEC(3);
+    if (gc0 >= c.N) continue;
+#pragma unroll
+    for (int j = 0; j < UNIT; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + col0 + j);
+      const float4 s4 = *reinterpret_cast<const float4*>(c.ss1 + col0 + j);
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float x = __fmaf_rn(ar, __fmaf_rn(nam, ss[e], v[j + e]), bb[e]);               // rho*(acc - mu*s1) + c0
+        if (fl.res)
+          x = __fadd_rn(__fmaf_rn(__half2float(reinterpret_cast<const __half*>(rl)[j + e]), F16_LO_INV, x),
+                        __half2float(reinterpret_cast<const __half*>(rh)[j + e]));
+        x = fmaxf(x, lo_clamp);
+        if (gc0 + j + e >= c.N) x = 0.f;                                               // ragged last column tile
+        v[j + e] = x;
+        rsum += x;
+        rsq = __fmaf_rn(x, x, rsq);
+      }
+    }
+    SEC(3);
+    const bool whole = gc0 + UNIT <= c.N;
+    if (fl.f32) {
+      if (c.row_ok) {
+        float* dst = c.o_f32 + c.orow * (size_t)c.N + gc0;
+        if (whole && wide) {
+          st_global_256(dst, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])),
+                        make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+          st_global_256(dst + 8, make_uint4(__float_as_uint(v[8]), __float_as_uint(v[9]), __float_as_uint(v[10]), __float_as_uint(v[11])),
+                        make_uint4(__float_as_uint(v[12]), __float_as_uint(v[13]), __float_as_uint(v[14]), __float_as_uint(v[15])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < UNIT; j += 4)                                            // N % 4 == 0
+            if (gc0 + j < c.N) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+    } else {
+      __half2 hh[UNIT / 2], ll[UNIT / 2];
+#pragma unroll
+      for (int j = 0; j < UNIT; j += 2) {
+        const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
+        const float2 hf = __half22float2(h2);
+        hh[j >> 1] = h2;
+        ll[j >> 1] = __floats2half2_rn(__fmul_rn(__fsub_rn(v[j], hf.x), F16_LO_SCALE),
+                                       __fmul_rn(__fsub_rn(v[j + 1], hf.y), F16_LO_SCALE));
+      }
+      __half* dh = c.o_hi + c.orow * (size_t)c.N + gc0;
+      __half* dl = c.o_lo + c.orow * (size_t)c.N + gc0;
+      const uint4* ph = reinterpret_cast<const uint4*>(hh);
+      const uint4* pl = reinterpret_cast<const uint4*>(ll);
+      if (whole && wide) {
+        st_global_256(dh, ph[0], ph[1]);
+        st_global_256(dl, pl[0], pl[1]);
+      } else {                                                                         // N % 8 == 0
+        *reinterpret_cast<uint4*>(dh) = ph[0]; *reinterpret_cast<uint4*>(dl) = pl[0];
+        if (gc0 + 8 < c.N) { *reinterpret_cast<uint4*>(dh + 8) = ph[1]; *reinterpret_cast<uint4*>(dl + 8) = pl[1]; }
+      }
+    }
+    SEC(5);
+  }
+  tmem_ld_wait();
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(c.tempty_leader);
+  if (fl.stats) {                                        // partial row sums of this warp's 64 columns
+    const size_t o = (size_t)(2 * c.ct + half) * c.stat_stride + c.srow;
+    c.out_sum[o] = rsum;
+    c.out_sq[o] = rsq;
+  }
+  SEC(6);
+#undef SEC
+}
+
+__global__ void __launch_bounds__(F_THREADS, 1)
+refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* bres = smem;
+  unsigned char* a_stages = smem + P_SMEM_B;
+  float* svec = reinterpret_cast<float*>(a_stages + F_SMEM_A);                    // [L][bias 128 | s1 128]
+  float2* sln = reinterpret_cast<float2*>(a_stages + F_SMEM_A + F_SMEM_VECS);     // [tile parity][row] (-mean, rstd)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_stages + F_SMEM_A + F_SMEM_VECS + F_SMEM_LN);
+  uint64_t* full = bars;
+  uint64_t* empty = full + F_STAGES;
+  uint64_t* wfull = empty + F_STAGES;
+  uint64_t* wfree = wfull + P_MAX_KB;
+  uint64_t* tfull = wfree + P_MAX_KB;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* ready = tempty + 2;
+  uint64_t* tdone = ready + F_MAX_SLOTS;
+  uint64_t* lnfull = tdone + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lnfull + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const uint32_t rank = crank & 1u;
+  const uint32_t leader = crank & ~1u;
+  const int ntile = p.ntile;
+  const int ct = (int)(crank >> 1), g = blockIdx.x / (2 * ntile);
+  const int col_base = ct * BN;
+  const int groups = p.groups;
+  const int nsp = (p.rows + 2 * BM - 1) / (2 * BM);
+  const int cnt = (nsp - g + groups - 1) / groups;        // strip pairs of this cluster: g, g + groups, ...
+  const int L = p.L, S = p.S;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < F_STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], (uint32_t)ntile); }
+    for (int k = 0; k < P_MAX_KB; ++k) { mbar_init(&wfull[k], 1); mbar_init(&wfree[k], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
+    for (int s = 0; s < F_MAX_SLOTS; ++s) mbar_init(&ready[s], (uint32_t)(2 * ntile));
+    for (int i = 0; i < 4; ++i) mbar_init(&tdone[i], EPI_WARPS);
+    for (int i = 0; i < 2; ++i) mbar_init(&lnfull[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+  for (int i = threadIdx.x; i < L * BN; i += F_THREADS) {        // this pair's 128 columns of every layer's vectors
+    const int l = i / BN, c = col_base + (i - l * BN);
+    const int N = (l == L - 1) ? p.D : p.Hd;
+    svec[l * 2 * BN + (i - l * BN)] = c < N ? __ldg(p.bias[l] + c) : 0.f;
+    svec[l * 2 * BN + BN + (i - l * BN)] = (p.s1[l] && c < N) ? __ldg(p.s1[l] + c) : 0.f;
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- activation producer (every CTA): one thread drives the barriers and the TMA.  It never does
+    // anything else: with three stages in flight any pause of this thread is a bubble in the tensor pipe.
+    if (lane == 0) for (int i = 0; i < 3; ++i) { prefetch_tensormap(&tm.a_hi[i]); prefetch_tensormap(&tm.a_lo[i]); }
+    uint16_t mc_mask = 0;
+    for (int j = 0; j < ntile; ++j) mc_mask |= (uint16_t)(1u << (2 * j + (int)rank));
+    const int nkb0 = (p.C + F_BK - 1) / F_BK;
+    int stage = 0; uint32_t phase = 0;
+    int turn = 0, nchunk = 0;
+    const bool dbg_on = p.dbg != nullptr;
+    long long w_ready = 0, w_empty = 0, tq = 0;
+    for (int c0 = 0; c0 < cnt; c0 += S, ++nchunk) {
+      const int Sc = min(S, cnt - c0);
+      for (int l = 0; l < L; ++l) {
+        const LayerInfo li = layer_info(p, l);
+        const int nkb = (li.K + F_BK - 1) / F_BK;            // stages per tile
+        const CUtensorMap* mh = &tm.a_hi[li.src];
+        const CUtensorMap* ml = &tm.a_lo[li.src];
+        for (int s = 0; s < Sc; ++s) {
+          const int srow0 = ((g * S + s) * 2 + (int)rank) * BM;
+          const int row0 = li.src == 0 ? (g + (c0 + s) * groups) * 2 * BM + (int)rank * BM : srow0;
+          if (l > 0) {
+            if (lane == 0) {
+              // every CTA of the cluster has stored its columns of this strip's previous layer and
+              // published them (release fence at cluster scope + arrival).  What follows reads the strip
+              // only through L2 (TMA here, ld.global.cg in the other warps), in program order after the
+              // wait: no cluster-scope acquire fence, which on this hardware is an invalidation of the
+              // whole L1 (CCTL.IVALL) and would evict the bias vectors the epilogue reads through it
+              // once per tile.  The proxy fence orders the async proxy (TMA) after the wait.
+              const uint32_t par = (uint32_t)(nchunk * (L - 1) + l - 1) & 1u;
+              if (dbg_on) tq = clock64();
+              mbar_wait(&ready[s], par);
+              if (dbg_on) w_ready += clock64() - tq;
+              fence_proxy_async_all();
+            }
+          }
+          if (lane == 0) {
+            const bool pf = (l == L - 1) && (c0 + S + s < cnt);   // next chunk's input rows -> L2
+            const int pf_row = (g + (c0 + S + s) * groups) * 2 * BM + (int)rank * BM;
+            for (int kb = 0; kb < nkb; ++kb) {
+              if (dbg_on) tq = clock64();
+              mbar_wait(&empty[stage], phase ^ 1);
+              if (dbg_on) w_empty += clock64() - tq;
+              unsigned char* st = a_stages + stage * F_STAGE_BYTES;
+              const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), leader);
+              if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * F_STAGE_BYTES);
+              else mbar_arrive_cluster(full_leader);
+              if (turn == ct) {
+                if (ntile == 1) {
+                  tma_load_2d_pair(st, mh, full_leader, kb * F_BK, row0);
+                  tma_load_2d_pair(st + F_HALF_BYTES, ml, full_leader, kb * F_BK, row0);
+                } else {
+                  tma_load_2d_pair_mc(st, mh, full_leader, kb * F_BK, row0, mc_mask);
+                  tma_load_2d_pair_mc(st + F_HALF_BYTES, ml, full_leader, kb * F_BK, row0, mc_mask);
+                }
+                if (pf && kb < nkb0) {
+                  tma_prefetch_l2_2d(&tm.a_hi[0], kb * F_BK, pf_row);
+                  tma_prefetch_l2_2d(&tm.a_lo[0], kb * F_BK, pf_row);
+                }
+              }
+              if (++turn == ntile) turn = 0;
+              if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+    if (lane == 0) {
+      for (int i = 0; i < F_STAGES; ++i) {                        // drain the last multicast commits (see gemm_pair_kernel)
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (dbg_on) { long long* d = p.dbg + 16 * blockIdx.x; d[4] = w_ready; d[5] = w_empty; }
+    }
+  } else if (warp == F_W_WARP) {
+    if (elect_one()) {                                            // ---- weight producer (every CTA)
+      const uint32_t wfull_leader0 = mapa_u32(smem_u32(&wfull[0]), leader);
+      uint32_t n = 0;                                             // running (chunk, layer) count
+      for (int c0 = 0; c0 < cnt; c0 += S) {
+        for (int l = 0; l < L; ++l, ++n) {
+          const LayerInfo li = layer_info(p, l);
+          const int nkb = (li.K + BK - 1) / BK;
+          prefetch_tensormap(&tm.w_hi[l]); prefetch_tensormap(&tm.w_lo[l]);
+          for (int kb = 0; kb < P_MAX_KB; ++kb) {
+            // the last strip of the previous layer has multiplied by this k-block of the old weights
+            if (n > 0) mbar_wait(&wfree[kb], (n - 1) & 1u);
+            if (kb < nkb) {
+              if (rank == 0) mbar_arrive_expect_tx(&wfull[kb], 2u * 2u * B_HALF);
+              tma_load_2d_pair(bres + kb * 2 * B_HALF, &tm.w_hi[l], wfull_leader0 + 8u * kb, kb * BK, col_base + (int)rank * 64);
+              tma_load_2d_pair(bres + kb * 2 * B_HALF + B_HALF, &tm.w_lo[l], wfull_leader0 + 8u * kb, kb * BK, col_base + (int)rank * 64);
+            } else if (rank == 0) {
+              mbar_arrive(&wfull[kb]);                            // keeps the phase count of unused k-blocks in step
+            }
+          }
+        }
+      }
+      // the last layer's wfree commits (multicast into this CTA) must have landed before the CTA may exit
+      for (int kb = 0; kb < P_MAX_KB; ++kb) mbar_wait(&wfree[kb], (n - 1) & 1u);
+    }
+  } else if (warp == F_PUB_WARP) {
+    // ---- publisher / LayerNorm warp.  Two jobs, both off the critical paths of the other warps:
+    //  P(l, s): when the eight epilogue warps have stored tile (l, s) (tdone), lane 0 issues ONE release
+    //           fence at cluster scope (cumulative over their stores) and one arrival per CTA of the
+    //           cluster on ready[s]; the fence's round trip to L2 is paid here, not by the epilogue;
+    //  N(l, s): once ready[s] of layer l-1 has completed, the warp turns the partial row sums of the
+    //           strip into the (-mean, rstd) pairs of this CTA's 128 rows (shared memory) and completes
+    //           lnfull[tile parity]; the epilogue threads then need one 8-byte shared load per tile.
+    // Order: N of the NEXT tile, then P of the current one (the next tile's scalars are ready a whole
+    // tile before its epilogue starts); with single-strip chunks the next tile depends on the current
+    // one, so P comes first.  Two (-mean, rstd) buffers, by tile parity: N(t + 1) overwrites what tile
+    // t - 1 read, and the P(t - 1) before it has waited for that tile's epilogue.
+    const uint32_t ncta = (uint32_t)(2 * ntile);
+    uint32_t tcn = 0, t = 0;                                      // published tiles / all tiles so far
+    int nchunk = 0;
+    auto ln_tile = [&](uint32_t t1, int nch, int l, int s) {      // N for the tile with running index t1
+      const LayerInfo li = layer_info(p, l);
+      if (l >= 1 && li.ln) {
+        if (lane == 0) {
+          mbar_wait(&ready[s], (uint32_t)(nch * (L - 1) + l - 1) & 1u);
+        }
+        __syncwarp();
+        const int srow0 = ((g * S + s) * 2 + (int)rank) * BM;
+        const float* ps = p.st_sum[li.st_in];
+        const float* pq = p.st_sq[li.st_in];
+        constexpr int MAXP = 2 * (P_MAX_KB * BK / BN);             // partial sums per row: two halves per column tile
+        float vs[BM / 32][MAXP], vq[BM / 32][MAXP];
+#pragma unroll
+        for (int rr = 0; rr < BM / 32; ++rr)                       // all loads first: one L2 round trip for the lot
+#pragma unroll
+          for (int i = 0; i < MAXP; ++i) {
+            const size_t o = (size_t)i * p.stat_stride + (size_t)(srow0 + rr * 32 + lane);
+            vs[rr][i] = i < 2 * ntile ? ld_cg_f32(ps + o) : 0.f;
+            vq[rr][i] = i < 2 * ntile ? ld_cg_f32(pq + o) : 0.f;
+          }
+#pragma unroll
+        for (int rr = 0; rr < BM / 32; ++rr) {                     // fixed order: halves of a column tile, then tiles
+          float sm = 0.f, sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < MAXP; i += 2)
+            if (i < 2 * ntile) { sm += vs[rr][i] + vs[rr][i + 1]; sq += vq[rr][i] + vq[rr][i + 1]; }
+          const float mean = sm / (float)li.K;
+          const float var = fmaxf(sq / (float)li.K - mean * mean, 0.f);
+          sln[(t1 & 1u) * BM + rr * 32 + lane] = make_float2(-mean, 1.0f / sqrtf(var + 1e-5f));
+        }
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(&lnfull[t1 & 1u]);               // one phase per tile, LayerNorm-fed or not
+    };
+    ln_tile(0, 0, 0, 0);
+    for (int c0 = 0; c0 < cnt; c0 += S, ++nchunk) {
+      const int Sc = min(S, cnt - c0);
+      for (int l = 0; l < L; ++l) {
+        for (int s = 0; s < Sc; ++s, ++t) {
+          // the tile that follows (l, s) in the cluster's order
+          int nch = nchunk, nl = l, ns = s + 1;
+          if (ns == Sc) { ns = 0; ++nl; }
+          if (nl == L) { nl = 0; ++nch; }
+          const bool have_next = nl < L && (nch == nchunk || c0 + S < cnt);
+          // it depends on the current tile only when the chunk has a single strip
+          const bool next_first = !(Sc == 1 && nch == nchunk);
+          if (have_next && next_first) ln_tile(t + 1, nch, nl, ns);
+          if (l + 1 < L) {                                        // P(l, s)
+            if (lane == 0) {
+              mbar_wait(&tdone[tcn & 3u], (tcn >> 2) & 1u);
+              asm volatile("fence.release.cluster;" ::: "memory");
+              const uint32_t rb = smem_u32(&ready[s]);
+              for (uint32_t j = 0; j < ncta; ++j) mbar_arrive_cluster_relaxed(mapa_u32(rb, j));
+            }
+            ++tcn;
+          }
+          if (have_next && !next_first) ln_tile(t + 1, nch, nl, ns);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {                               // ---- MMA issuer (leader CTA of each pair)
+      const uint32_t idesc = make_instr_desc(FMT_F16, 2 * BM, BN);
+      const uint16_t pair_mask = (uint16_t)(3u << leader);
+      const uint16_t all_mask = (uint16_t)((1u << (2 * ntile)) - 1u);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t tc = 0, n = 0;
+      const bool dbg_on = p.dbg != nullptr;
+      long long w_full = 0, w_tempty = 0, w_w = 0, tq = 0;
+      const long long t_begin = clock64();
+      for (int c0 = 0; c0 < cnt; c0 += S) {
+        const int Sc = min(S, cnt - c0);
+        for (int l = 0; l < L; ++l, ++n) {
+          const LayerInfo li = layer_info(p, l);
+          const int nkb = (li.K + BK - 1) / BK;               // weight k-blocks of this layer
+          for (int s = 0; s < Sc; ++s, ++tc) {
+            const int acc = (int)(tc & 1u);
+            if (dbg_on) tq = clock64();
+            mbar_wait(&tempty[acc], ((tc >> 1) & 1u) ^ 1u);
+            if (dbg_on) w_tempty += clock64() - tq;
+            tcgen05_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * 2 * BN;
+            const uint32_t tmem_s = tmem_d + BN;
+            const bool last_strip = s == Sc - 1;
+            const int nst = (li.K + F_BK - 1) / F_BK;             // activation stages of this tile (32 K-elements each)
+            for (int ks = 0; ks < nst; ++ks) {
+              const int kb = ks / F_SUB, sub = ks % F_SUB;        // weight k-block (64 K-elements) of this stage
+              if (dbg_on) tq = clock64();
+              if (s == 0 && sub == 0) mbar_wait(&wfull[kb], n & 1u);     // this layer's weights, k-block kb
+              if (dbg_on) { const long long t1 = clock64(); w_w += t1 - tq; tq = t1; }
+              mbar_wait(&full[stage], phase);
+              if (dbg_on) w_full += clock64() - tq;
+              tcgen05_fence_after();
+              const uint32_t sa = smem_u32(a_stages + stage * F_STAGE_BYTES);
+              const uint32_t sb = smem_u32(bres + kb * 2 * B_HALF);
+              const uint64_t a_hi = F_BK == 64 ? make_smem_desc_sw128(sa) : make_smem_desc_sw64(sa);
+              const uint64_t a_lo = F_BK == 64 ? make_smem_desc_sw128(sa + F_HALF_BYTES) : make_smem_desc_sw64(sa + F_HALF_BYTES);
+              const uint64_t boff = (uint64_t)(sub * F_BK * 2 >> 4);      // position inside the 128-byte weight rows
+              const uint64_t b_hi = make_smem_desc_sw128(sb) + boff;
+              const uint64_t b_lo = make_smem_desc_sw128(sb + B_HALF) + boff;
+#pragma unroll
+              for (int k = 0; k < F_BK / 16; ++k) {
+                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                const uint32_t first = (ks | k) ? 1u : 0u;
+                umma_ss_pair(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
+                umma_ss_pair(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma_ss_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+              }
+              tcgen05_commit_pair(&empty[stage], all_mask);
+              if (last_strip && (sub == F_SUB - 1 || ks == nst - 1)) tcgen05_commit_pair(&wfree[kb], pair_mask);
+              if (ks == nst - 1) tcgen05_commit_pair(&tfull[acc], pair_mask);
+              if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (last_strip)
+              for (int kb = nkb; kb < P_MAX_KB; ++kb) tcgen05_commit_pair(&wfree[kb], pair_mask);
+          }
+        }
+      }
+      if (dbg_on) {
+        long long* d = p.dbg + 16 * blockIdx.x;
+        d[0] = clock64() - t_begin; d[1] = w_full; d[2] = w_tempty; d[3] = w_w;
+      }
+    }
+  } else {
+    // ---- epilogue warps 2..9 of both CTAs
+    EpiTile c;
+    c.tmem_base = tmem_base;
+    c.q = warp & 3;
+    const int ew = warp - 2;
+    c.half = ew >> 2;
+    c.lane = lane; c.ct = ct; c.col_base = col_base;
+    c.o_f32 = p.raw;
+    c.res_h = p.s_hi[0]; c.res_l = p.s_lo[0];
+    c.stat_stride = p.stat_stride;
+    c.tfull = tfull;
+    const uint32_t tempty_leader0 = mapa_u32(smem_u32(&tempty[0]), leader);
+    const uint32_t tempty_leader1 = mapa_u32(smem_u32(&tempty[1]), leader);
+    uint32_t tc = 0;
+#ifdef SSLAM_FUSED_SECTIONS
+    long long sec[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+    c.dbg_wait = (p.dbg && lane == 0 && (warp == 2 || warp == 6)) ? sec : nullptr;
+#else
+    c.dbg_wait = nullptr;
+#endif
+    uint32_t tcn = 0;                                             // tiles handed to the publisher so far
+    int nchunk = 0;
+    for (int c0 = 0; c0 < cnt; c0 += S, ++nchunk) {
+      const int Sc = min(S, cnt - c0);
+      for (int l = 0; l < L; ++l) {
+        const LayerInfo li = layer_info(p, l);
+        c.N = li.N; c.K = li.K;
+        c.sbias = svec + l * 2 * BN; c.ss1 = c.sbias + BN;
+        c.o_hi = p.s_hi[li.dst]; c.o_lo = p.s_lo[li.dst];
+        c.out_sum = p.st_sum[li.st_out]; c.out_sq = p.st_sq[li.st_out];
+        for (int s = 0; s < Sc; ++s, ++tc) {
+          const int srow_w = ((g * S + s) * 2 + (int)rank) * BM + c.q * 32;       // scratch row of lane 0
+          const int trow_w = (g + (c0 + s) * groups) * 2 * BM + (int)rank * BM + c.q * 32;
+          c.srow = (size_t)(srow_w + lane);
+          c.orow = li.f32 ? (size_t)(trow_w + lane) : c.srow;
+          c.row_ok = trow_w + lane < p.rows;
+          const int acc = (int)(tc & 1u);
+          const uint32_t par = (tc >> 1) & 1u;
+          c.tempty_leader = acc ? tempty_leader1 : tempty_leader0;
+          const EpiFlags fl{li.ln, li.res, li.relu, li.f32, li.stats};
+          c.ln = sln + (tc & 1u) * BM;
+          c.lnfull = &lnfull[tc & 1u];
+          c.ln_parity = (tc >> 1) & 1u;
+          fused_epilogue_tile(c, fl, acc, par);
+          if (l < L - 1) {                                        // hand the tile to the publisher warp
+            if (p.dbg_flags & 1) __threadfence();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tdone[tcn & 3u]);
+            ++tcn;
+          }
+        }
+      }
+    }
+#ifdef SSLAM_FUSED_SECTIONS
+    if (c.dbg_wait && warp == 2) {
+      long long* d = p.dbg + 16 * blockIdx.x + 6;
+      d[0] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) d[1 + i] = sec[i];
+    }
+#endif
   }
   tcgen05_fence_before();
   cluster_sync_all();
@@ -844,6 +1505,97 @@ int launch_gemm(Pair a, Pair w, int rows, int N, int K, const float* bias, RowSt
   return SSLAM_OK;
 }
 
+// ---- host side of the fused kernel
+bool fused_eligible(int C, int Hd, int D, int blocks) {
+  const int nt = (Hd + BN - 1) / BN;
+  return g_refiner_fused > 0 && C <= P_MAX_KB * BK && Hd <= P_MAX_KB * BK && D <= nt * BN &&
+         2 + 2 * blocks <= F_MAX_LAYERS;
+}
+// upper bound of the scratch rows: clusters that can be co-resident (<= 160 SMs / cluster size) x S x 256
+size_t fused_scratch_rows(int rows, int Hd) {
+  const size_t nt = (size_t)(Hd + BN - 1) / BN;
+  const size_t nsp = ((size_t)rows + 2 * BM - 1) / (2 * BM);
+  const size_t cap = 160 / (2 * nt);
+  return (nsp < cap ? nsp : cap) * F_MAX_SLOTS * 2 * BM;
+}
+size_t fused_scratch_bytes(int rows, int Hd) {
+  const size_t r = fused_scratch_rows(rows, Hd), nt = (size_t)(Hd + BN - 1) / BN;
+  return 2 * 2 * align_up(r * Hd * 2, 256) + 4 * align_up(2 * nt * r * 4, 256) + 1024;
+}
+
+struct FusedLayer { Pair w; const float* bias; const float* s1; };
+
+int launch_fused(Pair xs, const FusedLayer* layers, int rows, int C, int Hd, int D, int blocks, float* raw,
+                 char* scratch, cudaStream_t stream) {
+  const int L = 2 + 2 * blocks;
+  const int ntile = (Hd + BN - 1) / BN;
+  const int nsp = (rows + 2 * BM - 1) / (2 * BM);
+  static std::atomic<int> max_clusters[64][5] = {};              // per device and cluster shape, 0 = not queried
+  int dev = 0;
+  SSLAM_CHECK_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2 * ntile; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(F_THREADS); cfg.dynamicSmemBytes = F_SMEM_TOTAL; cfg.stream = stream;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  int mcl = max_clusters[dev][ntile].load();
+  if (mcl == 0) {
+    SSLAM_CHECK_CUDA(cudaFuncSetAttribute(refiner_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_TOTAL));
+    cfg.gridDim = dim3(2 * ntile);
+    SSLAM_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&mcl, refiner_fused_kernel, &cfg));
+    SSLAM_REQUIRE(mcl >= 1, SSLAM_EUNSUPPORTED, "refiner: no cluster of %d CTAs fits on this device", 2 * ntile);
+    max_clusters[dev][ntile].store(mcl);
+  }
+  int groups = mcl < nsp ? mcl : nsp;
+  const int cap = 160 / (2 * ntile);
+  if (groups > cap) groups = cap;
+  int S = g_refiner_fused & 255;
+  if (S > F_MAX_SLOTS) S = F_MAX_SLOTS;
+  const int per_cluster = (nsp + groups - 1) / groups;
+  if (S > per_cluster) S = per_cluster;                          // short inputs: no unused scratch slots
+  const size_t srows = (size_t)groups * S * 2 * BM;
+  SSLAM_REQUIRE(srows <= fused_scratch_rows(rows, Hd), SSLAM_EWORKSPACE, "refiner: fused scratch too small");
+
+  // scratch: h pair, u pair, four partial-sum arrays
+  char* wp = scratch;
+  auto take = [&](size_t bytes) { char* q = wp; wp += align_up(bytes, 256); return q; };
+  Pair sh{reinterpret_cast<__half*>(take(srows * Hd * 2)), nullptr};
+  sh.lo = reinterpret_cast<__half*>(take(srows * Hd * 2));
+  Pair su{reinterpret_cast<__half*>(take(srows * Hd * 2)), nullptr};
+  su.lo = reinterpret_cast<__half*>(take(srows * Hd * 2));
+  FusedParams fp = {};
+  for (int i = 0; i < 2; ++i) {
+    fp.st_sum[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4));
+    fp.st_sq[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4));
+  }
+  fp.rows = rows; fp.C = C; fp.Hd = Hd; fp.D = D; fp.L = L; fp.S = S; fp.groups = groups; fp.ntile = ntile;
+  fp.s_hi[0] = sh.hi; fp.s_lo[0] = sh.lo; fp.s_hi[1] = su.hi; fp.s_lo[1] = su.lo; fp.raw = raw; fp.stat_stride = srows;
+  fp.dbg = g_gemm_dbg;
+  fp.dbg_flags = g_refiner_fused >> 8;
+
+  FusedMaps m;
+  int rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[0], xs.hi, rows, C, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[0], xs.lo, rows, C, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[1], sh.hi, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[1], sh.lo, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[2], su.hi, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[2], su.lo, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  for (int l = 0; l < F_MAX_LAYERS; ++l) {
+    const int ll = l < L ? l : L - 1;                            // unused entries alias a valid map
+    const int K = ll == 0 ? C : Hd, N = ll == L - 1 ? D : Hd;
+    if ((rc = make_tensor_map_2d(&m.w_hi[l], layers[ll].w.hi, N, K, 64, BK, 2))) return rc;
+    if ((rc = make_tensor_map_2d(&m.w_lo[l], layers[ll].w.lo, N, K, 64, BK, 2))) return rc;
+    fp.bias[l] = layers[ll].bias;
+    fp.s1[l] = layers[ll].s1;
+  }
+  cfg.gridDim = dim3(2u * ntile * groups);
+  SSLAM_LAUNCH(KK_GEMM, stream, cudaLaunchKernelEx(&cfg, refiner_fused_kernel, m, fp));
+  return SSLAM_OK;
+}
+
 // packed weights: per Linear the fp16 hi then lo copies of the [out, in] matrix; the LayerNorm-fed
 // ones (fc1, fc2 of every block) are stored folded and followed by s1[out], c0[out] (fp32)
 size_t pair_bytes(size_t n) { return 2 * align_up(n * 2, 256); }
@@ -905,7 +1657,8 @@ extern "C" size_t sslam_refiner_workspace_bytes(int rows, int C, int Hd, int D, 
   if (rows <= 0) return 0;
   const size_t r = (size_t)rows;
   // pairs (4 B/element): x [r,C]; h_a, h_b, u [r,Hd];  fp32 raw [r,D];  3 sets of partial row sums
-  return (r * C + 3 * r * Hd + r * D) * 4 + 6 * (size_t)stat_parts_of(Hd) * stat_stride_of(rows) * 4 + 16 * 256;
+  return (r * C + 3 * r * Hd + r * D) * 4 + 6 * (size_t)stat_parts_of(Hd) * stat_stride_of(rows) * 4 + 16 * 256 +
+         fused_scratch_bytes(rows, Hd);
 }
 
 extern "C" int sslam_refiner_forward_f32(const float* const* params, const void* packed, const float* x,
@@ -941,6 +1694,7 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   Pair xs = take_pair(r * C), h_a = take_pair(r * Hd), h_b = take_pair(r * Hd), u = take_pair(r * Hd);
   RowStats st_a = take_stats(), st_b = take_stats(), st_u = take_stats();
   float* raw = reinterpret_cast<float*>(wp);
+  char* fused_scratch = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(wp) + r * D * 4, 256));
   const char* pk = static_cast<const char*>(packed);
   auto next_w = [&](size_t n) {
     Pair q{reinterpret_cast<__half*>(const_cast<char*>(pk)),
@@ -956,6 +1710,23 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
   } else {                                                                // pair written by the gather kernel
     xs.hi = static_cast<__half*>(const_cast<void*>(x_hi));
     xs.lo = static_cast<__half*>(const_cast<void*>(x_lo));
+  }
+  if (fused_eligible(C, Hd, D, blocks)) {
+    // one persistent launch for all layers (refiner_fused_kernel); activations stay in L2
+    FusedLayer layers[F_MAX_LAYERS];
+    int nl = 0;
+    layers[nl++] = FusedLayer{next_w((size_t)Hd * C), params[1], nullptr};
+    for (int b = 0; b < blocks; ++b)
+      for (int half = 0; half < 2; ++half) {
+        const Pair wl = next_w((size_t)Hd * Hd);
+        const float* s1 = reinterpret_cast<const float*>(pk);
+        const float* c0 = reinterpret_cast<const float*>(pk + align_up((size_t)Hd * 4, 256));
+        pk += vec_bytes(Hd);
+        layers[nl++] = FusedLayer{wl, c0, s1};
+      }
+    layers[nl++] = FusedLayer{next_w((size_t)D * Hd), params[3 + 8 * blocks], nullptr};
+    if ((rc = launch_fused(xs, layers, rows, C, Hd, D, blocks, raw, fused_scratch, stream))) return rc;
+    return sslam_l2norm_rows(raw, rows, D, eps_norm, out_f32, out_bf16, out_hi, out_lo, stream_);   // :86
   }
   Pair w = next_w((size_t)Hd * C);                                        // descriptor_refiner.py:76
   if ((rc = launch_gemm(xs, w, rows, Hd, C, params[1], no_stats, nullptr, none, 1, nullptr, h_a,
@@ -993,6 +1764,10 @@ extern "C" int sslam_refiner_forward_f32(const float* const* params, const void*
 // wait_tempty, wait_weights; epilogue warp 2: total, wait_tfull, wait_store, tiles}, 8 int64 per CTA)
 // are written to buf (device) while buf != NULL.
 extern "C" void sslam_debug_gemm_stalls(long long* buf) { sslam::g_gemm_dbg = buf; }
+
+// Debug aid for tests / tools: 0 = one GEMM launch per layer (gemm_pair_kernel); 1..4 = the layer-fused
+// kernel with that many strip pairs per chunk (default 3).
+extern "C" void sslam_debug_refiner_fused(int mode) { sslam::g_refiner_fused = mode < 0 ? 0 : mode; }
 
 // Debug aid for tools/: host-mapped buffer (device pointer) that receives watchdog records of this
 // translation unit's kernels; see tc_common.cuh.

@@ -67,6 +67,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // in this host-mapped buffer before trapping.  One copy per translation unit.
 static __device__ unsigned long long* g_watchdog_buf = nullptr;
 
+// cold path of mbar_wait, out of line (it used to be inlined at every wait: ~40 instructions per site)
+static __device__ __noinline__ void mbar_wait_timeout_check(uint32_t addr, uint32_t parity, unsigned long long& t0) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (t0 == 0) { t0 = now; return; }
+  if (now - t0 > (threadIdx.x < 64 ? 1500000000ull : 2000000000ull)) {   // control warps report first
+    if (g_watchdog_buf) {
+      const bool ctl = threadIdx.x < 64;               // producer / MMA warps first
+      const unsigned long long slot = atomicAdd(g_watchdog_buf + (ctl ? 1 : 0), 1ull);
+      if (slot < (ctl ? 30ull : 32ull)) {
+        uint32_t crank;
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        g_watchdog_buf[(ctl ? 2 : 32) + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 36) |
+                                   ((unsigned long long)(crank & 15) << 32) | ((unsigned long long)(addr & 0xffffff) << 4) |
+                                   (parity & 1);
+      }
+      __threadfence_system();
+    }
+    __trap();
+  }
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok = 0;
@@ -82,26 +104,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity), "r"(100000u)
         : "memory");
-    if (!ok && (spin & 63u) == 63u) {
-      unsigned long long now;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > (threadIdx.x < 64 ? 1500000000ull : 2000000000ull)) {   // control warps report first
-        if (g_watchdog_buf) {
-          const bool ctl = threadIdx.x < 64;               // producer / MMA warps first
-          const unsigned long long slot = atomicAdd(g_watchdog_buf + (ctl ? 1 : 0), 1ull);
-          if (slot < (ctl ? 30ull : 32ull)) {
-            uint32_t crank;
-            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
-            g_watchdog_buf[(ctl ? 2 : 32) + slot] = ((unsigned long long)blockIdx.x << 48) | ((unsigned long long)threadIdx.x << 36) |
-                                       ((unsigned long long)(crank & 15) << 32) | ((unsigned long long)(addr & 0xffffff) << 4) |
-                                       (parity & 1);
-          }
-          __threadfence_system();
-        }
-        __trap();
-      }
-    }
+    if (!ok && (spin & 63u) == 63u) mbar_wait_timeout_check(addr, parity, t0);
   }
 }
 

@@ -250,6 +250,55 @@ def test_refiner_fused_vs_oracle_and_torch(dev):
     assert np.abs(out - z["out"]).max() < 1e-5
 
 
+def test_refiner_layer_fused_equals_per_layer(dev):
+    """The layer-fused persistent kernel (refiner_fused_kernel: activations exchanged through L2, weights
+    switched per layer) performs the arithmetic of the per-layer GEMM launches in the same order: outputs are
+    bit-identical for every chunk depth S = 1..4, ragged row counts, several chunks per cluster, 0..3
+    residual blocks and partial column tiles."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import _lib
+    lib = _lib.load()
+    torch.manual_seed(1)
+    try:
+        for (C, Hd, D, layers, rows) in ((384, 384, 256, 4, 40), (384, 384, 256, 4, 2048 + 77), (384, 384, 256, 4, 30000),
+                                         (384, 384, 128, 4, 6000), (64, 96, 32, 2, 130), (48, 64, 32, 5, 9000),
+                                         (384, 384, 256, 5, 23000), (320, 264, 200, 3, 12345), (384, 384, 256, 4, 200000)):
+            m = DescriptorRefiner(C, Hd, D, layers).to(dev).eval()
+            with torch.no_grad():
+                for blk in m.residual_blocks:                 # non-trivial LayerNorm affine parameters
+                    for ln in (blk.norm1, blk.norm2):
+                        ln.weight.uniform_(0.5, 1.5)
+                        ln.bias.uniform_(-0.3, 0.3)
+            g = torch.Generator().manual_seed(rows)
+            x = torch.randn(1, rows, C, generator=g).to(dev)
+            lib.sslam_debug_refiner_fused(0)
+            with torch.no_grad():
+                ref = m(x).clone()
+            for S in (1, 2, 3, 4):
+                lib.sslam_debug_refiner_fused(S)
+                with torch.no_grad():
+                    out = m(x)
+                torch.cuda.synchronize()
+                assert torch.equal(out, ref), (C, Hd, D, layers, rows, S, float((out - ref).abs().max()))
+    finally:
+        lib.sslam_debug_refiner_fused(3)
+
+
+def test_refiner_layer_fused_back_to_back(dev):
+    """200 launches of the fused kernel in a row on c2-sized chunks give the same bits every time (the
+    cluster protocol — multicast stages, weight switch, ready barriers — leaves no state behind)."""
+    from models.descriptor_refiner import DescriptorRefiner
+    torch.manual_seed(2)
+    m = DescriptorRefiner(384, 384, 256, 4).to(dev).eval()
+    x = torch.randn(1, 50 * 2048, 384, device=dev)
+    with torch.no_grad():
+        ref = m(x).clone()
+        for _ in range(200):
+            out = m(x)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+
+
 def test_gather_pair_output(dev):
     """gather_bilinear(pair=True): fp16 (hi, lo) operands reproduce the fp32 sample to 22 bits."""
     from sslam_b200 import ops
