@@ -221,7 +221,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
       const bool row_ok = grow < p.rows;
       float am = 0.f, ar = 0.f;                         // folded-LN scalars of this row
       if (p.a_sum && row_ok) row_layernorm_scalars(p, grow, am, ar);
-      float rsum = 0.f, rsq = 0.f;
+      float rsum2[2] = {0.f, 0.f}, rsq2[2] = {0.f, 0.f};   // row sums of the even / odd columns (as the packed fused epilogue)
       // residual of one unit = this row's 16 values of each half of the pair; requested one unit
       // ahead so that its HBM latency overlaps the arithmetic of the current unit
       auto unit_col = [&](int ct_, int un_) {
@@ -281,8 +281,8 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
               if (p.relu) x = fmaxf(x, 0.f);
               if (!cok) x = 0.f;
               v[j + e] = x;
-              rsum += x;
-              rsq = __fmaf_rn(x, x, rsq);
+              rsum2[e & 1] += x;
+              rsq2[e & 1] = __fmaf_rn(x, x, rsq2[e & 1]);
             }
           }
           // the previous TMA store of this warp must have finished reading the staging box
@@ -321,7 +321,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         // row sums of what this strip stored: combine the two column halves of each row
         float* sc = stats + (sidx & 1) * (4 * 32 * 2 * 2);
         float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
-        e[0] = rsum; e[1] = rsq;
+        e[0] = rsum2[0] + rsum2[1]; e[1] = rsq2[0] + rsq2[1];
         named_bar_sync(1, 32 * EPI_WARPS);
         if (half == 0 && row_ok) {
           const float* f = sc + (q * 32 + lane) * 4;
@@ -547,7 +547,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
       const bool row_ok = grow < p.rows;
       float am = 0.f, ar = 0.f, nam = 0.f;
       if (LN && row_ok) { row_layernorm_scalars(p, grow, am, ar); nam = -am; }
-      float rsum = 0.f, rsq = 0.f;
+      float rsum2[2] = {0.f, 0.f}, rsq2[2] = {0.f, 0.f};   // row sums of the even / odd columns (as the packed fused epilogue)
       // residual of one unit = this row's 16 values of each half of the pair, requested one unit ahead
       const __half* res_h = RES ? p.res_hi + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
       const __half* res_l = RES ? p.res_lo + (size_t)(row_ok ? grow : 0) * p.N : nullptr;
@@ -649,7 +649,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         }
         if (STATS) {
 #pragma unroll
-          for (int j = 0; j < UNIT; ++j) { rsum += v[j]; rsq = __fmaf_rn(v[j], v[j], rsq); }
+          for (int j = 0; j < UNIT; ++j) { rsum2[j & 1] += v[j]; rsq2[j & 1] = __fmaf_rn(v[j], v[j], rsq2[j & 1]); }
         }
         if (lane == 0) tma_store_wait_read<0>();        // previous box of this warp has left smem
         __syncwarp();
@@ -692,7 +692,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         // partial row sums of this column tile: combine the two 64-column halves of each row
         float* sc = stats + (tc & 1) * (4 * 32 * 2 * 2);
         float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
-        e[0] = rsum; e[1] = rsq;
+        e[0] = rsum2[0] + rsum2[1]; e[1] = rsq2[0] + rsq2[1];
         named_bar_sync(1, 32 * EPI_WARPS);
         if (half == 0 && row_ok) {
           const float* f = sc + (q * 32 + lane) * 4;
@@ -750,9 +750,11 @@ constexpr int F_PUB_WARP = F_W_WARP + 1;
 // i.e. the feed is not short of bytes in flight: both the per-layer kernel and this one settle at about
 // 192 KB of A operand per 8.5 - 9k cycles and SM (~22 B/clk).
 constexpr int F_BK = 64;
+constexpr int SCR_CHUNK = (BM / 8) * 64;                   // elements per 8-column chunk of a 128-row scratch strip (16 core matrices)
 constexpr int F_HALF_BYTES = BM * F_BK * 2;               // one 128-row operand tile of a stage
 constexpr int F_STAGE_BYTES = 2 * F_HALF_BYTES;           // A_hi, A_lo
-constexpr int F_STAGES = F_BK == 64 ? 3 : 7;
+static_assert(F_BK == 64, "the stage of the fused kernel is one 64-column block");
+constexpr int F_STAGES = 3;
 constexpr int F_SUB = BK / F_BK;                          // stages per 64-element weight k-block
 constexpr int F_SMEM_A = F_STAGES * F_STAGE_BYTES;
 constexpr int F_SMEM_VECS = F_MAX_LAYERS * 2 * BN * 4;    // [layer][bias 128 | s1 128] of the pair's columns
@@ -826,7 +828,8 @@ struct EpiTile {
   uint32_t tmem_base;
   int q, half, lane, ct, col_base;
   int N, K;                          // layer's output width / LayerNorm width
-  size_t srow;                       // this thread's scratch row (statistics, residual)
+  size_t srow;                       // this thread's scratch row (statistics)
+  size_t soff;                       // element offset of (this row, column 0) in a scratch array (core-matrix layout)
   size_t orow;                       // this thread's row in the output array (scratch row, or true row for the last layer)
   bool row_ok;                       // last layer: orow < rows
   const float* sbias;                // this layer's 128 bias / c0 values of the pair's columns (shared memory)
@@ -843,6 +846,7 @@ struct EpiTile {
   float* out_sq;
   size_t stat_stride;
   long long* dbg_wait;               // debug: per-section cycle counters (null = off)
+  bool nostore;                      // debug: skip the output stores
   uint64_t* tfull;
   uint32_t tempty_leader;
 };
@@ -874,28 +878,29 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
   long long* const dw = c.dbg_wait;
   long long t0 = 0;
 #ifdef SSLAM_FUSED_SECTIONS                                // build-time switch of tools/fused_probe.py's section timers
+#if SSLAM_FUSED_SECTIONS == 2                               // coarse: [0] wait for the accumulator, [6] the rest of the tile
+#define SEC(i) do { if (dw && ((i) == 0 || (i) == 6)) { const long long t1_ = clock64(); dw[i] += t1_ - t0; t0 = t1_; } } while (0)
+#else
 #define SEC(i) do { if (dw) { const long long t1_ = clock64(); dw[i] += t1_ - t0; t0 = t1_; } } while (0)
+#endif
   if (dw) t0 = clock64();
 #else
 #define SEC(i) do { } while (0)
   (void)dw; (void)t0;
 #endif
   const float lo_clamp = fl.relu ? 0.f : __int_as_float(0xff800000);
-  float rsum = 0.f, rsq = 0.f;
-  const __half* res_h = c.res_h + c.srow * (size_t)c.N;
-  const __half* res_l = c.res_l + c.srow * (size_t)c.N;
-  const bool wide = (c.N & 15) == 0;                     // rows are 32-byte aligned only when N % 16 == 0
+  const bool wide = (c.N & 15) == 0;                     // fp32 output rows are 32-byte aligned only when N % 16 == 0
+  // scratch arrays (h, u) are stored as 8-row x 16-byte core matrices, [strip][column / 8][row / 8][row % 8][column % 8]:
+  // a thread's 8 columns of a chunk are 16 contiguous bytes and the 32 rows of a warp make 512 contiguous
+  // bytes per chunk, so every load / store instruction of the warp moves four whole 128-byte lines
+  const __half* res_h = c.res_h + c.soff;
+  const __half* res_l = c.res_l + c.soff;
   uint4 nh[2], nl[2];
   nh[0] = nh[1] = nl[0] = nl[1] = make_uint4(0u, 0u, 0u, 0u);
   auto load_res = [&](int gc) {
-    if (gc + UNIT <= c.N && wide) {
-      ld_cg_256(res_h + gc, nh);
-      ld_cg_256(res_l + gc, nl);
-    } else {
-      nh[0] = nh[1] = nl[0] = nl[1] = make_uint4(0u, 0u, 0u, 0u);
-      if (gc < c.N) { nh[0] = ld_cg_128(res_h + gc); nl[0] = ld_cg_128(res_l + gc); }
-      if (gc + 8 < c.N) { nh[1] = ld_cg_128(res_h + gc + 8); nl[1] = ld_cg_128(res_l + gc + 8); }
-    }
+    const size_t o = (size_t)(gc >> 3) * SCR_CHUNK;
+    if (gc < c.N) { nh[0] = ld_cg_128(res_h + o); nl[0] = ld_cg_128(res_l + o); }
+    if (gc + 8 < c.N) { nh[1] = ld_cg_128(res_h + o + SCR_CHUNK); nl[1] = ld_cg_128(res_l + o + SCR_CHUNK); }
   };
   if (fl.res) load_res(c.col_base + half * 64);          // in flight while the accumulator completes
   SEC(1);
@@ -915,47 +920,67 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
   const uint32_t tbase = c.tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + half * 64;
   tmem_ld_32x16(tbase, r);
   tmem_ld_32x16(tbase + BN, rs);
+  // The arithmetic below is the scalar formula of gemm_pair_kernel's epilogue, element for element
+  // (same operations, same roundings), issued two elements at a time: FFMA2 / FADD2 / FMUL2 on register
+  // pairs, and the fp16 <-> fp32 mixed forms (FHADD, FHFMA) instead of a conversion plus an fp32 operation.
+  // The epilogue is issue bound (two warps per scheduler): this halves its instruction count.
+  const uint64_t inv2 = pack_f32x2(F16_LO_INV, F16_LO_INV), ar2 = pack_f32x2(ar, ar), nam2 = pack_f32x2(nam, nam);
+  const uint64_t msc2 = pack_f32x2(-F16_LO_SCALE, -F16_LO_SCALE);
+  uint64_t sum2 = pack_f32x2(0.f, 0.f), sq2 = sum2;      // row sums of the even / odd columns
 #pragma unroll
   for (int un = 0; un < 64 / UNIT; ++un) {
     const int col0 = half * 64 + un * UNIT;
     const int gc0 = c.col_base + col0;
     uint4 rh[2] = {nh[0], nh[1]}, rl[2] = {nl[0], nl[1]};
     if (fl.res && un + 1 < 64 / UNIT) load_res(gc0 + UNIT);
-    float v[UNIT];
+    uint64_t x2[UNIT / 2];
     SEC(3);
     tmem_ld_wait();
     SEC(2);
 #pragma unroll
-    for (int j = 0; j < UNIT; ++j)
-      v[j] = __fmaf_rn(__uint_as_float(rs[j]), F16_LO_INV, __uint_as_float(r[j]));     // fold the cross terms
+    for (int j = 0; j < UNIT / 2; ++j)                     // fold the cross terms
+      x2[j] = ffma2(pack_f32x2(__uint_as_float(rs[2 * j]), __uint_as_float(rs[2 * j + 1])), inv2,
+                    pack_f32x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
     if (un + 1 < 64 / UNIT) {                            // next unit's accumulators: in flight during the math
       tmem_ld_32x16(tbase + (un + 1) * UNIT, r);
       tmem_ld_32x16(tbase + (un + 1) * UNIT + BN, rs);
     }
     SEC(3);
     if (gc0 >= c.N) continue;
+    float v[UNIT];
 #pragma unroll
-    for (int j = 0; j < UNIT; j += 4) {
-      const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + col0 + j);
-      const float4 s4 = *reinterpret_cast<const float4*>(c.ss1 + col0 + j);
-      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-      const float ss[4] = {s4.x, s4.y, s4.z, s4.w};
+    for (int j = 0; j < UNIT / 2; j += 2) {
+      const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + col0 + 2 * j);
+      const float4 s4 = *reinterpret_cast<const float4*>(c.ss1 + col0 + 2 * j);
+      // rho*(acc - mu*s1) + c0
+      x2[j] = ffma2(ar2, ffma2(nam2, pack_f32x2(s4.x, s4.y), x2[j]), pack_f32x2(b4.x, b4.y));
+      x2[j + 1] = ffma2(ar2, ffma2(nam2, pack_f32x2(s4.z, s4.w), x2[j + 1]), pack_f32x2(b4.z, b4.w));
+    }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float x = __fmaf_rn(ar, __fmaf_rn(nam, ss[e], v[j + e]), bb[e]);               // rho*(acc - mu*s1) + c0
-        if (fl.res)
-          x = __fadd_rn(__fmaf_rn(__half2float(reinterpret_cast<const __half*>(rl)[j + e]), F16_LO_INV, x),
-                        __half2float(reinterpret_cast<const __half*>(rh)[j + e]));
-        x = fmaxf(x, lo_clamp);
-        if (gc0 + j + e >= c.N) x = 0.f;                                               // ragged last column tile
-        v[j + e] = x;
-        rsum += x;
-        rsq = __fmaf_rn(x, x, rsq);
-      }
+    for (int j = 0; j < UNIT / 2; ++j) unpack_f32x2(x2[j], v[2 * j], v[2 * j + 1]);
+    if (fl.res) {
+      const uint16_t* ph = reinterpret_cast<const uint16_t*>(rh);
+      const uint16_t* pl = reinterpret_cast<const uint16_t*>(rl);
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) v[j] = fhadd(ph[j], fhfma(pl[j], F16_LO_INV_BITS, v[j]));   // + (hi + lo * 2^-11)
+    }
+#pragma unroll
+    for (int j = 0; j < UNIT; ++j) v[j] = fmaxf(v[j], lo_clamp);
+    if (gc0 + UNIT > c.N) {                                // ragged last column tile (warp-uniform)
+#pragma unroll
+      for (int j = 0; j < UNIT; ++j) if (gc0 + j >= c.N) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < UNIT / 2; ++j) {
+      x2[j] = pack_f32x2(v[2 * j], v[2 * j + 1]);
+      sum2 = fadd2(sum2, x2[j]);
+      sq2 = ffma2(x2[j], x2[j], sq2);
     }
     SEC(3);
     const bool whole = gc0 + UNIT <= c.N;
-    if (fl.f32) {
+    if (c.nostore) {
+      if (v[0] == 1234.5f) c.o_f32[0] = v[3] + v[7] + v[12];
+    } else if (fl.f32) {
       if (c.row_ok) {
         float* dst = c.o_f32 + c.orow * (size_t)c.N + gc0;
         if (whole && wide) {
@@ -970,28 +995,37 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
         }
       }
     } else {
-      __half2 hh[UNIT / 2], ll[UNIT / 2];
+      uint32_t hh[UNIT / 2], ll[UNIT / 2];
 #pragma unroll
-      for (int j = 0; j < UNIT; j += 2) {
-        const __half2 h2 = __floats2half2_rn(v[j], v[j + 1]);
-        const float2 hf = __half22float2(h2);
-        hh[j >> 1] = h2;
-        ll[j >> 1] = __floats2half2_rn(__fmul_rn(__fsub_rn(v[j], hf.x), F16_LO_SCALE),
-                                       __fmul_rn(__fsub_rn(v[j + 1], hf.y), F16_LO_SCALE));
+      for (int j = 0; j < UNIT / 2; ++j) {
+        const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+        const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h2);
+        hh[j] = hu;
+        // (v - hi) * 2^11 as (hi - v) * -2^11: both steps exact
+        const uint64_t d2 = fmul2(pack_f32x2(fhadd((uint16_t)(hu & 0xffffu), -v[2 * j]), fhadd((uint16_t)(hu >> 16), -v[2 * j + 1])), msc2);
+        float d0, d1;
+        unpack_f32x2(d2, d0, d1);
+        const __half2 l2 = __floats2half2_rn(d0, d1);
+        ll[j] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      __half* dh = c.o_hi + c.orow * (size_t)c.N + gc0;
-      __half* dl = c.o_lo + c.orow * (size_t)c.N + gc0;
+      const size_t o = c.soff + (size_t)(gc0 >> 3) * SCR_CHUNK;
       const uint4* ph = reinterpret_cast<const uint4*>(hh);
       const uint4* pl = reinterpret_cast<const uint4*>(ll);
-      if (whole && wide) {
-        st_global_256(dh, ph[0], ph[1]);
-        st_global_256(dl, pl[0], pl[1]);
-      } else {                                                                         // N % 8 == 0
-        *reinterpret_cast<uint4*>(dh) = ph[0]; *reinterpret_cast<uint4*>(dl) = pl[0];
-        if (gc0 + 8 < c.N) { *reinterpret_cast<uint4*>(dh + 8) = ph[1]; *reinterpret_cast<uint4*>(dl + 8) = pl[1]; }
+      *reinterpret_cast<uint4*>(c.o_hi + o) = ph[0];                                   // N % 8 == 0
+      *reinterpret_cast<uint4*>(c.o_lo + o) = pl[0];
+      if (gc0 + 8 < c.N) {
+        *reinterpret_cast<uint4*>(c.o_hi + o + SCR_CHUNK) = ph[1];
+        *reinterpret_cast<uint4*>(c.o_lo + o + SCR_CHUNK) = pl[1];
       }
     }
     SEC(5);
+  }
+  float rsum, rsq;
+  {
+    float a0, a1, q0, q1;
+    unpack_f32x2(sum2, a0, a1);
+    unpack_f32x2(sq2, q0, q1);
+    rsum = a0 + a1; rsq = q0 + q1;
   }
   tmem_ld_wait();
   tcgen05_fence_before();
@@ -1066,6 +1100,7 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
     uint16_t mc_mask = 0;
     for (int j = 0; j < ntile; ++j) mc_mask |= (uint16_t)(1u << (2 * j + (int)rank));
     const int nkb0 = (p.C + F_BK - 1) / F_BK;
+    const int scr_kb = (p.Hd + F_BK - 1) / F_BK;                  // 64-column blocks of a scratch strip
     int stage = 0; uint32_t phase = 0;
     int turn = 0, nchunk = 0;
     const bool dbg_on = p.dbg != nullptr;
@@ -1107,12 +1142,16 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
               if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2u * F_STAGE_BYTES);
               else mbar_arrive_cluster(full_leader);
               if (turn == ct) {
+                // x: box of the row-major pair (128 rows x 64 columns, 128-byte swizzle); h / u: the stage is
+                // 16 KB of contiguous memory (8 chunks of the strip), fetched as 16 rows of 1 KB of a flat map
+                const int c0x = li.src == 0 ? kb * F_BK : 0;
+                const int c1x = li.src == 0 ? row0 : (srow0 / BM) * scr_kb * (F_HALF_BYTES / 1024) + kb * (F_HALF_BYTES / 1024);
                 if (ntile == 1) {
-                  tma_load_2d_pair(st, mh, full_leader, kb * F_BK, row0);
-                  tma_load_2d_pair(st + F_HALF_BYTES, ml, full_leader, kb * F_BK, row0);
+                  tma_load_2d_pair(st, mh, full_leader, c0x, c1x);
+                  tma_load_2d_pair(st + F_HALF_BYTES, ml, full_leader, c0x, c1x);
                 } else {
-                  tma_load_2d_pair_mc(st, mh, full_leader, kb * F_BK, row0, mc_mask);
-                  tma_load_2d_pair_mc(st + F_HALF_BYTES, ml, full_leader, kb * F_BK, row0, mc_mask);
+                  tma_load_2d_pair_mc(st, mh, full_leader, c0x, c1x, mc_mask);
+                  tma_load_2d_pair_mc(st + F_HALF_BYTES, ml, full_leader, c0x, c1x, mc_mask);
                 }
                 if (pf && kb < nkb0) {
                   tma_prefetch_l2_2d(&tm.a_hi[0], kb * F_BK, pf_row);
@@ -1268,18 +1307,23 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
               tcgen05_fence_after();
               const uint32_t sa = smem_u32(a_stages + stage * F_STAGE_BYTES);
               const uint32_t sb = smem_u32(bres + kb * 2 * B_HALF);
-              const uint64_t a_hi = F_BK == 64 ? make_smem_desc_sw128(sa) : make_smem_desc_sw64(sa);
-              const uint64_t a_lo = F_BK == 64 ? make_smem_desc_sw128(sa + F_HALF_BYTES) : make_smem_desc_sw64(sa + F_HALF_BYTES);
+              // x tiles are 128-byte-swizzled rows; h / u tiles are core matrices (no swizzle): next chunk
+              // of K at +2048 bytes, next 8 rows at +128 bytes, a k-step (two chunks) every 4096 bytes
+              const bool cm = li.src != 0;
+              const uint64_t a_hi = cm ? make_smem_desc_interleave(sa, 2048, 128) : make_smem_desc_sw128(sa);
+              const uint64_t a_lo = cm ? make_smem_desc_interleave(sa + F_HALF_BYTES, 2048, 128) : make_smem_desc_sw128(sa + F_HALF_BYTES);
+              const uint64_t a_step = cm ? (uint64_t)(4096 >> 4) : (uint64_t)(32 >> 4);
               const uint64_t boff = (uint64_t)(sub * F_BK * 2 >> 4);      // position inside the 128-byte weight rows
               const uint64_t b_hi = make_smem_desc_sw128(sb) + boff;
               const uint64_t b_lo = make_smem_desc_sw128(sb + B_HALF) + boff;
+              if (!(p.dbg_flags & 2))
 #pragma unroll
               for (int k = 0; k < F_BK / 16; ++k) {
-                const uint64_t adv = (uint64_t)(k * 32 >> 4);
+                const uint64_t adv = (uint64_t)(k * 32 >> 4), aadv = (uint64_t)k * a_step;
                 const uint32_t first = (ks | k) ? 1u : 0u;
-                umma_ss_pair(tmem_s, a_lo + adv, b_hi + adv, idesc, first);
-                umma_ss_pair(tmem_s, a_hi + adv, b_lo + adv, idesc, 1u);
-                umma_ss_pair(tmem_d, a_hi + adv, b_hi + adv, idesc, first);
+                umma_ss_pair(tmem_s, a_lo + aadv, b_hi + adv, idesc, first);
+                umma_ss_pair(tmem_s, a_hi + aadv, b_lo + adv, idesc, 1u);
+                umma_ss_pair(tmem_d, a_hi + aadv, b_hi + adv, idesc, first);
               }
               tcgen05_commit_pair(&empty[stage], all_mask);
               if (last_strip && (sub == F_SUB - 1 || ks == nst - 1)) tcgen05_commit_pair(&wfree[kb], pair_mask);
@@ -1320,6 +1364,7 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
 #endif
     uint32_t tcn = 0;                                             // tiles handed to the publisher so far
     int nchunk = 0;
+    const size_t scr_strip = (size_t)((p.Hd + F_BK - 1) / F_BK) * 8 * SCR_CHUNK;   // elements of one strip of a scratch array
     for (int c0 = 0; c0 < cnt; c0 += S, ++nchunk) {
       const int Sc = min(S, cnt - c0);
       for (int l = 0; l < L; ++l) {
@@ -1332,16 +1377,26 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
           const int srow_w = ((g * S + s) * 2 + (int)rank) * BM + c.q * 32;       // scratch row of lane 0
           const int trow_w = (g + (c0 + s) * groups) * 2 * BM + (int)rank * BM + c.q * 32;
           c.srow = (size_t)(srow_w + lane);
+          c.soff = (size_t)((g * S + s) * 2 + (int)rank) * scr_strip + (size_t)(((c.q * 32 + lane) >> 3) * 64 + (lane & 7) * 8);
           c.orow = li.f32 ? (size_t)(trow_w + lane) : c.srow;
           c.row_ok = trow_w + lane < p.rows;
           const int acc = (int)(tc & 1u);
           const uint32_t par = (tc >> 1) & 1u;
           c.tempty_leader = acc ? tempty_leader1 : tempty_leader0;
-          const EpiFlags fl{li.ln, li.res, li.relu, li.f32, li.stats};
+          const EpiFlags fl{li.ln && !(p.dbg_flags & 32), li.res && !(p.dbg_flags & 16), li.relu, li.f32, li.stats && !(p.dbg_flags & 64)};
+          c.nostore = (p.dbg_flags & 8) != 0;
           c.ln = sln + (tc & 1u) * BM;
           c.lnfull = &lnfull[tc & 1u];
           c.ln_parity = (tc >> 1) & 1u;
-          fused_epilogue_tile(c, fl, acc, par);
+          if (p.dbg_flags & 4) {
+            mbar_wait(&tfull[acc], par);
+            tcgen05_fence_after();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(c.tempty_leader);
+          } else {
+            fused_epilogue_tile(c, fl, acc, par);
+          }
           if (l < L - 1) {                                        // hand the tile to the publisher warp
             if (p.dbg_flags & 1) __threadfence();
             __syncwarp();
@@ -1520,7 +1575,8 @@ size_t fused_scratch_rows(int rows, int Hd) {
 }
 size_t fused_scratch_bytes(int rows, int Hd) {
   const size_t r = fused_scratch_rows(rows, Hd), nt = (size_t)(Hd + BN - 1) / BN;
-  return 2 * 2 * align_up(r * Hd * 2, 256) + 4 * align_up(2 * nt * r * 4, 256) + 1024;
+  const size_t hd_pad = (size_t)(Hd + F_BK - 1) / F_BK * F_BK;     // strips hold whole 64-column blocks
+  return 2 * 2 * align_up(r * hd_pad * 2, 1024) + 4 * align_up(2 * nt * r * 4, 256) + 2048;
 }
 
 struct FusedLayer { Pair w; const float* bias; const float* s1; };
@@ -1558,17 +1614,21 @@ int launch_fused(Pair xs, const FusedLayer* layers, int rows, int C, int Hd, int
   const size_t srows = (size_t)groups * S * 2 * BM;
   SSLAM_REQUIRE(srows <= fused_scratch_rows(rows, Hd), SSLAM_EWORKSPACE, "refiner: fused scratch too small");
 
-  // scratch: h pair, u pair, four partial-sum arrays
-  char* wp = scratch;
-  auto take = [&](size_t bytes) { char* q = wp; wp += align_up(bytes, 256); return q; };
-  Pair sh{reinterpret_cast<__half*>(take(srows * Hd * 2)), nullptr};
-  sh.lo = reinterpret_cast<__half*>(take(srows * Hd * 2));
-  Pair su{reinterpret_cast<__half*>(take(srows * Hd * 2)), nullptr};
-  su.lo = reinterpret_cast<__half*>(take(srows * Hd * 2));
+  // scratch: h pair, u pair (core-matrix layout, see fused_epilogue_tile: per 128-row strip
+  // [column / 8][row / 8][row % 8][column % 8], columns padded to whole 64-column blocks), four partial-sum arrays
+  const size_t hd_pad = (size_t)(Hd + F_BK - 1) / F_BK * F_BK;
+  char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(scratch), 1024));
+  auto take = [&](size_t bytes, size_t al) { char* q = wp; wp += align_up(bytes, al); return q; };
+  Pair sh{reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024)), nullptr};
+  sh.lo = reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024));
+  Pair su{reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024)), nullptr};
+  su.lo = reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024));
+  if (hd_pad != (size_t)Hd)     // the pad columns are multiplied (by zero weights): they must not hold NaN / Inf bit patterns
+    SSLAM_CHECK_CUDA(cudaMemsetAsync(sh.hi, 0, 4 * align_up(srows * hd_pad * 2, 1024), stream));
   FusedParams fp = {};
   for (int i = 0; i < 2; ++i) {
-    fp.st_sum[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4));
-    fp.st_sq[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4));
+    fp.st_sum[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4, 256));
+    fp.st_sq[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4, 256));
   }
   fp.rows = rows; fp.C = C; fp.Hd = Hd; fp.D = D; fp.L = L; fp.S = S; fp.groups = groups; fp.ntile = ntile;
   fp.s_hi[0] = sh.hi; fp.s_lo[0] = sh.lo; fp.s_hi[1] = su.hi; fp.s_lo[1] = su.lo; fp.raw = raw; fp.stat_stride = srows;
@@ -1577,12 +1637,14 @@ int launch_fused(Pair xs, const FusedLayer* layers, int rows, int C, int Hd, int
 
   FusedMaps m;
   int rc;
-  if ((rc = make_tensor_map_2d(&m.a_hi[0], xs.hi, rows, C, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_lo[0], xs.lo, rows, C, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_hi[1], sh.hi, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_lo[1], sh.lo, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_hi[2], su.hi, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_lo[2], su.lo, srows, Hd, BM, F_BK, 2, F_BK == 64 ? 128 : 64))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[0], xs.hi, rows, C, BM, F_BK, 2, 128))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[0], xs.lo, rows, C, BM, F_BK, 2, 128))) return rc;
+  // scratch arrays as flat memory: rows of 1 KB (256 words), a stage = 16 consecutive rows, no swizzle
+  const uint64_t flat_rows = srows * hd_pad * 2 / 1024;
+  if ((rc = make_tensor_map_2d(&m.a_hi[1], sh.hi, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[1], sh.lo, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[2], su.hi, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_lo[2], su.lo, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
   for (int l = 0; l < F_MAX_LAYERS; ++l) {
     const int ll = l < L ? l : L - 1;                            // unused entries alias a valid map
     const int K = ll == 0 ? C : Hd, N = ll == L - 1 ? D : Hd;

@@ -232,6 +232,17 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr) {
   d |= (uint64_t)4 << 61;
   return d;
 }
+// K-major operand tile WITHOUT swizzle ("interleaved" canonical layout): 8-row x 16-byte core matrices of
+// 128 contiguous bytes; `lbo` = byte distance between the two core matrices of a 32-byte k-step (next 8
+// elements of K), `sbo` = byte distance between consecutive 8-row groups.  Layout type 0.
+__device__ __forceinline__ uint64_t make_smem_desc_interleave(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(lbo >> 4) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
 // Instruction descriptor (32 bit) for kind::f16 / kind::tf32, dense, fp32 accumulate, both
 // operands K-major:  [4,6) D format 1=f32   [7,10) A format   [10,13) B format
 //   (0 f16, 1 bf16, 2 tf32)   [15] A major 0=K   [16] B major 0=K   [17,23) N>>3   [24,29) M>>4
@@ -355,6 +366,45 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
 __device__ __forceinline__ float join_f16(__half hi, __half lo) {
   return __fmaf_rn(__half2float(lo), F16_LO_INV, __half2float(hi));
 }
+// ---- two fp32 operations per instruction (sm_100: FFMA2 / FADD2 / FMUL2 on aligned register pairs) and
+// the mixed fp16 (+) fp32 forms (FHADD, FHFMA): each lane / operation is the IEEE round-to-nearest one,
+// so results are bit-identical to the scalar sequences they replace
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// fp32(h) + c
+__device__ __forceinline__ float fhadd(uint16_t h, float c) {
+  float r;
+  asm("add.rn.f32.f16 %0, %1, %2;" : "=f"(r) : "h"(h), "f"(c));
+  return r;
+}
+// fp32(a) * fp32(b) + c, one rounding
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {
+  float r;
+  asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(r) : "h"(a), "h"(b), "f"(c));
+  return r;
+}
+constexpr uint16_t F16_LO_INV_BITS = 0x1000;   // 2^-11 as fp16
 #endif  // __CUDACC__
 
 }  // namespace tc

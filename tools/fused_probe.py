@@ -39,8 +39,8 @@ for S in [int(v) for v in os.environ.get("MODES", "2,3,4").split(",")]:
     print("  MMA thread  : total %.0f cyc = %.0f per tile; wait A %.0f, wait accumulator free %.0f, wait weights %.0f (per tile)"
           % (lead[:, 0].mean(), lead[:, 0].mean() / ntiles, lead[:, 1].mean() / ntiles, lead[:, 2].mean() / ntiles, lead[:, 3].mean() / ntiles))
     print("  A producer  : wait ready %.0f, wait stage empty %.0f (per tile)" % (used[:, 4].mean() / ntiles, used[:, 5].mean() / ntiles))
-    names = ["wait acc full", "LN stats / residual issue", "tmem ld wait", "math + wait_read", "publish: wait_group", "pack + TMA store",
-             "stats tail", "publish"]
+    names = ["wait acc full", "residual issue", "tmem ld wait", "math (+ LN scalars wait)", "-", "split + stores",
+             "tail (coarse build: whole tile body)", "-"]
     print("  epilogue w2 : total %.0f per tile: " % (used[:, 6].mean() / ntiles)
           + ", ".join("%s %.0f" % (n, used[:, 7 + i].mean() / ntiles) for i, n in enumerate(names)))
 lib.sslam_debug_refiner_fused(3)

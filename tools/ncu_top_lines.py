@@ -22,11 +22,16 @@ for l in dis.splitlines():
     m = re.match(r"\s*/\*([0-9a-f]{4,6})\*/\s+(\S.*?);", l)
     if m and line:
         off2line[int(m.group(1), 16)] = line
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kname, "-c", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
 h = {n: i for i, n in enumerate(rows[hi])}
 data = rows[hi + 1:]
+for i_, r_ in enumerate(data):          # several launches in the report: keep the first
+    if r_ and r_[0] == "Kernel Name":
+        data = data[:i_]
+        break
+data = [r_ for r_ in data if r_ and r_[0].startswith("0x")]
 def num(x):
     try: return float(x)
     except Exception: return 0.0
