@@ -750,9 +750,20 @@ constexpr int F_PUB_WARP = F_W_WARP + 1;
 // i.e. the feed is not short of bytes in flight: both the per-layer kernel and this one settle at about
 // 192 KB of A operand per 8.5 - 9k cycles and SM (~22 B/clk).
 constexpr int F_BK = 64;
-constexpr int SCR_CHUNK = (BM / 8) * 64;                   // elements per 8-column chunk of a 128-row scratch strip (16 core matrices)
+// Scratch activations (h, u): per 128-row strip and 64-column block one 32 KB piece = exactly one stage of
+// the A operand, [hi | lo][column / 8 (8 chunks)][row / 8][row % 8][column % 8] — the no-swizzle core-matrix
+// layout of the UMMA descriptor.  A stage is ONE contiguous multicast request; a thread's 8 columns of a chunk
+// are 16 contiguous bytes and the 32 rows of a warp 512 contiguous bytes.
+constexpr int SCR_CHUNK = (BM / 8) * 64;                   // elements per 8-column chunk (16 core matrices)
+constexpr int SCR_PART = 8 * SCR_CHUNK;                    // elements of the hi (or lo) part of a 64-column block
+constexpr int SCR_BLOCK = 2 * SCR_PART;                    // elements of a 64-column block of a strip (32 KB)
+__device__ __forceinline__ size_t scr_off(int gc) {        // element offset of column gc (a multiple of 8) inside a strip's hi part
+  return (size_t)(gc >> 6) * SCR_BLOCK + (size_t)((gc >> 3) & 7) * SCR_CHUNK;
+}
 constexpr int F_HALF_BYTES = BM * F_BK * 2;               // one 128-row operand tile of a stage
 constexpr int F_STAGE_BYTES = 2 * F_HALF_BYTES;           // A_hi, A_lo
+// (7 stages of 32 columns, 8 KB per request: 3.4 ms instead of 2.9 — the cost of a multicast request is about
+// 160 cycles + 1 cycle per 73 bytes, so the feed wants few, large requests)
 static_assert(F_BK == 64, "the stage of the fused kernel is one 64-column block");
 constexpr int F_STAGES = 3;
 constexpr int F_SUB = BK / F_BK;                          // stages per 64-element weight k-block
@@ -847,6 +858,7 @@ struct EpiTile {
   size_t stat_stride;
   long long* dbg_wait;               // debug: per-section cycle counters (null = off)
   bool nostore;                      // debug: skip the output stores
+  int dbgf;                          // debug flags (128: free-running epilogue, 256: no TMEM loads)
   uint64_t* tfull;
   uint32_t tempty_leader;
 };
@@ -898,13 +910,13 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
   uint4 nh[2], nl[2];
   nh[0] = nh[1] = nl[0] = nl[1] = make_uint4(0u, 0u, 0u, 0u);
   auto load_res = [&](int gc) {
-    const size_t o = (size_t)(gc >> 3) * SCR_CHUNK;
+    const size_t o = scr_off(gc);
     if (gc < c.N) { nh[0] = ld_cg_128(res_h + o); nl[0] = ld_cg_128(res_l + o); }
     if (gc + 8 < c.N) { nh[1] = ld_cg_128(res_h + o + SCR_CHUNK); nl[1] = ld_cg_128(res_l + o + SCR_CHUNK); }
   };
   if (fl.res) load_res(c.col_base + half * 64);          // in flight while the accumulator completes
   SEC(1);
-  mbar_wait(&c.tfull[acc], tfull_parity);
+  if (!(c.dbgf & 128)) mbar_wait(&c.tfull[acc], tfull_parity);
   SEC(0);
   tcgen05_fence_after();
   // (-mean, rstd) of this row of the A operand, from the publisher / LayerNorm warp (normally complete a
@@ -912,14 +924,16 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
   // statistics of the strip's previous layer)
   float ar = 1.f, nam = -0.f;
   if (fl.ln) {
-    mbar_wait(c.lnfull, c.ln_parity);
+    if (!(c.dbgf & 128)) mbar_wait(c.lnfull, c.ln_parity);
     const float2 ln = c.ln[q * 32 + lane];
     nam = ln.x; ar = ln.y;
   }
   uint32_t r[UNIT], rs[UNIT];
   const uint32_t tbase = c.tmem_base + ((uint32_t)(q * 32) << 16) + acc * 2 * BN + half * 64;
-  tmem_ld_32x16(tbase, r);
-  tmem_ld_32x16(tbase + BN, rs);
+  if (!(c.dbgf & 256)) {
+    tmem_ld_32x16(tbase, r);
+    tmem_ld_32x16(tbase + BN, rs);
+  }
   // The arithmetic below is the scalar formula of gemm_pair_kernel's epilogue, element for element
   // (same operations, same roundings), issued two elements at a time: FFMA2 / FADD2 / FMUL2 on register
   // pairs, and the fp16 <-> fp32 mixed forms (FHADD, FHFMA) instead of a conversion plus an fp32 operation.
@@ -941,7 +955,7 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
     for (int j = 0; j < UNIT / 2; ++j)                     // fold the cross terms
       x2[j] = ffma2(pack_f32x2(__uint_as_float(rs[2 * j]), __uint_as_float(rs[2 * j + 1])), inv2,
                     pack_f32x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])));
-    if (un + 1 < 64 / UNIT) {                            // next unit's accumulators: in flight during the math
+    if (un + 1 < 64 / UNIT && !(c.dbgf & 256)) {         // next unit's accumulators: in flight during the math
       tmem_ld_32x16(tbase + (un + 1) * UNIT, r);
       tmem_ld_32x16(tbase + (un + 1) * UNIT + BN, rs);
     }
@@ -950,8 +964,11 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
     float v[UNIT];
 #pragma unroll
     for (int j = 0; j < UNIT / 2; j += 2) {
-      const float4 b4 = *reinterpret_cast<const float4*>(c.sbias + col0 + 2 * j);
-      const float4 s4 = *reinterpret_cast<const float4*>(c.ss1 + col0 + 2 * j);
+      float4 b4 = make_float4(0.5f, 0.25f, 0.125f, 1.f), s4 = b4;
+      if (!(c.dbgf & 512)) {
+        b4 = *reinterpret_cast<const float4*>(c.sbias + col0 + 2 * j);
+        s4 = *reinterpret_cast<const float4*>(c.ss1 + col0 + 2 * j);
+      }
       // rho*(acc - mu*s1) + c0
       x2[j] = ffma2(ar2, ffma2(nam2, pack_f32x2(s4.x, s4.y), x2[j]), pack_f32x2(b4.x, b4.y));
       x2[j + 1] = ffma2(ar2, ffma2(nam2, pack_f32x2(s4.z, s4.w), x2[j + 1]), pack_f32x2(b4.z, b4.w));
@@ -1008,7 +1025,7 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
         const __half2 l2 = __floats2half2_rn(d0, d1);
         ll[j] = *reinterpret_cast<const uint32_t*>(&l2);
       }
-      const size_t o = c.soff + (size_t)(gc0 >> 3) * SCR_CHUNK;
+      const size_t o = c.soff + scr_off(gc0);
       const uint4* ph = reinterpret_cast<const uint4*>(hh);
       const uint4* pl = reinterpret_cast<const uint4*>(ll);
       *reinterpret_cast<uint4*>(c.o_hi + o) = ph[0];                                   // N % 8 == 0
@@ -1093,7 +1110,9 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  const bool freerun = (p.dbg_flags & 128) != 0;       // debug: only the epilogue warps run, without any barrier
+  if (freerun && (warp < 2 || warp == F_W_WARP || warp == F_PUB_WARP)) {
+  } else if (warp == 0) {
     // ---- activation producer (every CTA): one thread drives the barriers and the TMA.  It never does
     // anything else: with three stages in flight any pause of this thread is a bubble in the tensor pipe.
     if (lane == 0) for (int i = 0; i < 3; ++i) { prefetch_tensormap(&tm.a_hi[i]); prefetch_tensormap(&tm.a_lo[i]); }
@@ -1145,8 +1164,11 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
                 // x: box of the row-major pair (128 rows x 64 columns, 128-byte swizzle); h / u: the stage is
                 // 16 KB of contiguous memory (8 chunks of the strip), fetched as 16 rows of 1 KB of a flat map
                 const int c0x = li.src == 0 ? kb * F_BK : 0;
-                const int c1x = li.src == 0 ? row0 : (srow0 / BM) * scr_kb * (F_HALF_BYTES / 1024) + kb * (F_HALF_BYTES / 1024);
-                if (ntile == 1) {
+                const int c1x = li.src == 0 ? row0 : ((srow0 / BM) * scr_kb + kb) * (F_STAGE_BYTES / 1024);
+                if (li.src != 0) {                              // one 32 KB request: hi and lo of the block
+                  if (ntile == 1) tma_load_2d_pair(st, mh, full_leader, 0, c1x);
+                  else tma_load_2d_pair_mc(st, mh, full_leader, 0, c1x, mc_mask);
+                } else if (ntile == 1) {
                   tma_load_2d_pair(st, mh, full_leader, c0x, c1x);
                   tma_load_2d_pair(st + F_HALF_BYTES, ml, full_leader, c0x, c1x);
                 } else {
@@ -1311,7 +1333,8 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
               // of K at +2048 bytes, next 8 rows at +128 bytes, a k-step (two chunks) every 4096 bytes
               const bool cm = li.src != 0;
               const uint64_t a_hi = cm ? make_smem_desc_interleave(sa, 2048, 128) : make_smem_desc_sw128(sa);
-              const uint64_t a_lo = cm ? make_smem_desc_interleave(sa + F_HALF_BYTES, 2048, 128) : make_smem_desc_sw128(sa + F_HALF_BYTES);
+              const uint64_t a_lo = cm ? make_smem_desc_interleave(sa + F_HALF_BYTES, 2048, 128)
+                                       : make_smem_desc_sw128(sa + F_HALF_BYTES);
               const uint64_t a_step = cm ? (uint64_t)(4096 >> 4) : (uint64_t)(32 >> 4);
               const uint64_t boff = (uint64_t)(sub * F_BK * 2 >> 4);      // position inside the 128-byte weight rows
               const uint64_t b_hi = make_smem_desc_sw128(sb) + boff;
@@ -1364,7 +1387,7 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
 #endif
     uint32_t tcn = 0;                                             // tiles handed to the publisher so far
     int nchunk = 0;
-    const size_t scr_strip = (size_t)((p.Hd + F_BK - 1) / F_BK) * 8 * SCR_CHUNK;   // elements of one strip of a scratch array
+    const size_t scr_strip = (size_t)((p.Hd + F_BK - 1) / F_BK) * SCR_BLOCK;   // elements of one strip of a scratch array
     for (int c0 = 0; c0 < cnt; c0 += S, ++nchunk) {
       const int Sc = min(S, cnt - c0);
       for (int l = 0; l < L; ++l) {
@@ -1385,6 +1408,7 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
           c.tempty_leader = acc ? tempty_leader1 : tempty_leader0;
           const EpiFlags fl{li.ln && !(p.dbg_flags & 32), li.res && !(p.dbg_flags & 16), li.relu, li.f32, li.stats && !(p.dbg_flags & 64)};
           c.nostore = (p.dbg_flags & 8) != 0;
+          c.dbgf = p.dbg_flags;
           c.ln = sln + (tc & 1u) * BM;
           c.lnfull = &lnfull[tc & 1u];
           c.ln_parity = (tc >> 1) & 1u;
@@ -1619,12 +1643,12 @@ int launch_fused(Pair xs, const FusedLayer* layers, int rows, int C, int Hd, int
   const size_t hd_pad = (size_t)(Hd + F_BK - 1) / F_BK * F_BK;
   char* wp = reinterpret_cast<char*>(align_up(reinterpret_cast<uintptr_t>(scratch), 1024));
   auto take = [&](size_t bytes, size_t al) { char* q = wp; wp += align_up(bytes, al); return q; };
-  Pair sh{reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024)), nullptr};
-  sh.lo = reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024));
-  Pair su{reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024)), nullptr};
-  su.lo = reinterpret_cast<__half*>(take(srows * hd_pad * 2, 1024));
+  Pair sh{reinterpret_cast<__half*>(take(srows * hd_pad * 4, 1024)), nullptr};
+  sh.lo = sh.hi + SCR_PART;
+  Pair su{reinterpret_cast<__half*>(take(srows * hd_pad * 4, 1024)), nullptr};
+  su.lo = su.hi + SCR_PART;
   if (hd_pad != (size_t)Hd)     // the pad columns are multiplied (by zero weights): they must not hold NaN / Inf bit patterns
-    SSLAM_CHECK_CUDA(cudaMemsetAsync(sh.hi, 0, 4 * align_up(srows * hd_pad * 2, 1024), stream));
+    SSLAM_CHECK_CUDA(cudaMemsetAsync(sh.hi, 0, 2 * align_up(srows * hd_pad * 4, 1024), stream));
   FusedParams fp = {};
   for (int i = 0; i < 2; ++i) {
     fp.st_sum[i] = reinterpret_cast<float*>(take((size_t)2 * ntile * srows * 4, 256));
@@ -1639,12 +1663,11 @@ int launch_fused(Pair xs, const FusedLayer* layers, int rows, int C, int Hd, int
   int rc;
   if ((rc = make_tensor_map_2d(&m.a_hi[0], xs.hi, rows, C, BM, F_BK, 2, 128))) return rc;
   if ((rc = make_tensor_map_2d(&m.a_lo[0], xs.lo, rows, C, BM, F_BK, 2, 128))) return rc;
-  // scratch arrays as flat memory: rows of 1 KB (256 words), a stage = 16 consecutive rows, no swizzle
-  const uint64_t flat_rows = srows * hd_pad * 2 / 1024;
-  if ((rc = make_tensor_map_2d(&m.a_hi[1], sh.hi, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_lo[1], sh.lo, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_hi[2], su.hi, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
-  if ((rc = make_tensor_map_2d(&m.a_lo[2], su.lo, flat_rows, 256, F_HALF_BYTES / 1024, 256, 4, 0))) return rc;
+  // scratch arrays as flat memory: rows of 1 KB (256 words), a stage = 32 consecutive rows, no swizzle
+  const uint64_t flat_rows = srows * hd_pad * 4 / 1024;
+  if ((rc = make_tensor_map_2d(&m.a_hi[1], sh.hi, flat_rows, 256, F_STAGE_BYTES / 1024, 256, 4, 0))) return rc;
+  if ((rc = make_tensor_map_2d(&m.a_hi[2], su.hi, flat_rows, 256, F_STAGE_BYTES / 1024, 256, 4, 0))) return rc;
+  m.a_lo[1] = m.a_hi[1]; m.a_lo[2] = m.a_hi[2];                  // (unused: one request fetches both parts)
   for (int l = 0; l < F_MAX_LAYERS; ++l) {
     const int ll = l < L ? l : L - 1;                            // unused entries alias a valid map
     const int K = ll == 0 ? C : Hd, N = ll == L - 1 ? D : Hd;
