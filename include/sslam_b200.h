@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SSLAM_ABI_VERSION 3
+#define SSLAM_ABI_VERSION 4
 
 enum {
   SSLAM_OK = 0,
@@ -37,7 +37,8 @@ enum {
   SSLAM_EUNSUPPORTED = -2, /* shape outside what the kernels implement (see each entry point)  */
   SSLAM_EWORKSPACE = -3,   /* workspace smaller than sslam_*_workspace_bytes()                 */
   SSLAM_ECUDA = -4,        /* a CUDA runtime call failed; text in sslam_last_error()           */
-  SSLAM_ENODEVICE = -5     /* no CUDA device of compute capability 10.x                        */
+  SSLAM_ENODEVICE = -5,    /* no CUDA device of compute capability 10.x                        */
+  SSLAM_ERANGE = -6        /* an activation left the fp16 range of the f16x3 arithmetic        */
 };
 
 /* decode `info` columns, int32 [B,4] */
@@ -164,6 +165,14 @@ int sslam_refiner_forward_f32(const float* const* params, const void* packed, co
                               int rows, int C, int Hd, int D, int blocks, float eps_norm,
                               float* out_f32, void* out_bf16, void* out_hi, void* out_lo,
                               void* ws, size_t ws_bytes, void* stream);
+/* Range guard of the fp16-pair arithmetic.  Every GEMM epilogue of sslam_refiner_forward_f32 watches the
+ * activations it stores: when the sum of squares of 64 consecutive columns of a row reaches 65504^2 (so at
+ * the latest when one |activation| >= 65504, where the fp16 hi part becomes inf), or is NaN / inf (which
+ * is also how an out-of-range INPUT shows up), a sticky flag is set on the device.  This call waits for
+ * `stream`, returns SSLAM_ERANGE if the flag was set by any forward on the current device since the last
+ * call (and clears it), SSLAM_OK otherwise.  The descriptors of a flagged forward are not to be used:
+ * run the fp32 PyTorch body (DescriptorRefiner(mlp="torch")) for such weights / inputs. */
+int sslam_refiner_range_check(void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Matching primitive shared by M1..M5: over the virtual S_p = D1_p . D2_p^T (never stored)

@@ -38,6 +38,10 @@ namespace sslam {
 
 using namespace tc;
 
+// sticky range flag of the fp16-pair arithmetic (sslam_refiner_range_check); one copy per device
+__device__ unsigned int g_refiner_status = 0;
+constexpr float F16_RANGE_SQ = 65504.0f * 65504.0f;
+
 long long* g_gemm_dbg = nullptr;    // set by sslam_debug_gemm_stalls (tools only, not part of the ABI)
 int g_refiner_fused = 3;            // 0: one launch per layer; 1..4: layer-fused kernel, strip pairs per chunk (sslam_debug_refiner_fused)
 
@@ -322,6 +326,7 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         float* sc = stats + (sidx & 1) * (4 * 32 * 2 * 2);
         float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
         e[0] = rsum2[0] + rsum2[1]; e[1] = rsq2[0] + rsq2[1];
+        if (!(e[1] < F16_RANGE_SQ)) atomicOr(&g_refiner_status, 1u);   // range guard (sslam_refiner_range_check)
         named_bar_sync(1, 32 * EPI_WARPS);
         if (half == 0 && row_ok) {
           const float* f = sc + (q * 32 + lane) * 4;
@@ -693,6 +698,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
         float* sc = stats + (tc & 1) * (4 * 32 * 2 * 2);
         float* e = sc + ((q * 32 + lane) * 2 + half) * 2;
         e[0] = rsum2[0] + rsum2[1]; e[1] = rsq2[0] + rsq2[1];
+        if (!(e[1] < F16_RANGE_SQ)) atomicOr(&g_refiner_status, 1u);   // range guard (sslam_refiner_range_check)
         named_bar_sync(1, 32 * EPI_WARPS);
         if (half == 0 && row_ok) {
           const float* f = sc + (q * 32 + lane) * 4;
@@ -1044,6 +1050,9 @@ __device__ __forceinline__ void fused_epilogue_tile(const EpiTile& c, const EpiF
     unpack_f32x2(sq2, q0, q1);
     rsum = a0 + a1; rsq = q0 + q1;
   }
+  // range guard: the pair just stored is garbage once an |x| reaches 65504 (x^2 alone then exceeds the
+  // bound; NaN / inf fail the comparison too)
+  if (!fl.f32 && !(rsq < F16_RANGE_SQ)) atomicOr(&g_refiner_status, 1u);
   tmem_ld_wait();
   tcgen05_fence_before();
   __syncwarp();
@@ -1852,6 +1861,23 @@ extern "C" void sslam_debug_gemm_stalls(long long* buf) { sslam::g_gemm_dbg = bu
 
 // Debug aid for tests / tools: 0 = one GEMM launch per layer (gemm_pair_kernel); 1..4 = the layer-fused
 // kernel with that many strip pairs per chunk (default 3).
+extern "C" int sslam_refiner_range_check(void* stream_) {
+  int rc = check_device();
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  unsigned int h = 0;
+  SSLAM_CHECK_CUDA(cudaMemcpyFromSymbolAsync(&h, sslam::g_refiner_status, sizeof(h), 0, cudaMemcpyDeviceToHost, stream));
+  SSLAM_CHECK_CUDA(cudaStreamSynchronize(stream));
+  if (h) {
+    const unsigned int zero = 0;
+    SSLAM_CHECK_CUDA(cudaMemcpyToSymbolAsync(sslam::g_refiner_status, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, stream));
+    SSLAM_CHECK_CUDA(cudaStreamSynchronize(stream));
+    SSLAM_REQUIRE(false, SSLAM_ERANGE,
+                  "refiner: an activation reached the fp16 range (|x| >= 65504, or NaN / inf) in the f16x3 arithmetic");
+  }
+  return SSLAM_OK;
+}
+
 extern "C" void sslam_debug_refiner_fused(int mode) { sslam::g_refiner_fused = mode < 0 ? 0 : mode; }
 
 // Debug aid for tools/: host-mapped buffer (device pointer) that receives watchdog records of this

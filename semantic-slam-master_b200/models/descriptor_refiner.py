@@ -54,6 +54,8 @@ class DescriptorRefiner(nn.Module):
         return self.output_proj(x)
 
     mlp = "tcgen05"          # "tcgen05" (default) or "torch" (cuBLAS fp32 body + l2norm kernel)
+    check_range = True       # forward(): synchronise and raise if an activation left the fp16 range of the
+                             # f16x3 arithmetic (the pipeline's forward_fused callers check once per run instead)
 
     def _ordered_params(self):
         ps = [self.input_proj.weight, self.input_proj.bias]
@@ -92,4 +94,7 @@ class DescriptorRefiner(nn.Module):
             return F.normalize(raw, p=2, dim=-1).reshape(B, N, self.output_dim)
         if self.mlp == "torch":
             return ops.l2norm_rows(self.forward_unnormalized(dino_features)).reshape(B, N, self.output_dim)
-        return self.forward_fused(dino_features).reshape(B, N, self.output_dim)
+        out = self.forward_fused(dino_features).reshape(B, N, self.output_dim)
+        if self.check_range and not torch.cuda.is_current_stream_capturing():
+            ops.refiner_range_check()      # no silent NaN: raises when an activation left the fp16 range
+        return out

@@ -34,6 +34,7 @@ SIGNATURES = {
     "sslam_refiner_forward_f32": (c_int, [ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_size_t, c_void_p]),
+    "sslam_refiner_range_check": (c_int, [c_void_p]),
     "sslam_match_workspace_bytes": (c_size_t, [c_int] * 7),
     "sslam_match_top2": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                  c_int, c_int, c_int,
@@ -67,10 +68,10 @@ DEBUG_SIGNATURES = {
 }
 
 ERROR_NAMES = {-1: "SSLAM_EINVAL", -2: "SSLAM_EUNSUPPORTED", -3: "SSLAM_EWORKSPACE",
-               -4: "SSLAM_ECUDA", -5: "SSLAM_ENODEVICE"}
+               -4: "SSLAM_ECUDA", -5: "SSLAM_ENODEVICE", -6: "SSLAM_ERANGE"}
 
 _lib = None
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class SslamError(RuntimeError):

@@ -217,6 +217,13 @@ def refiner_forward(plan, x, eps=1e-12, want_bf16=False, workspace=None, out=Non
     return (out, out16) if want_bf16 else out
 
 
+def refiner_range_check():
+    """Waits for the current stream and raises SslamError(SSLAM_ERANGE) if a refiner forward on this device
+    stored an activation outside the fp16 range of the f16x3 arithmetic (|x| >= 65504, NaN or inf) since the
+    last check; such descriptors must not be used (run DescriptorRefiner with mlp="torch").  Not capturable."""
+    _lib.check(_lib.load().sslam_refiner_range_check(_stream()))
+
+
 def match_top2(bank1, bank2, pair_index=None, mode=SIM_F16X3, num_pairs=None, workspace=None):
     """Row top-2 / column argmax of S_p = D1_p . D2_p^T without storing S.
 

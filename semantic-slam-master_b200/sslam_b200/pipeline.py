@@ -129,6 +129,14 @@ class FrontEnd:
         pairs, pscores, counts = self.match_consecutive(feats, variant, timers=timers, **kw)
         return feats, pairs, pscores, counts
 
+    def check_range(self):
+        """Raises if a refiner forward since the last check left the fp16 range of the f16x3 arithmetic
+        (ops.refiner_range_check; synchronises).  The device-resident entry points stay asynchronous and
+        capturable: call this once after run_sequence / run_pairs when the weights are not known to be
+        safe; the host entry points call it themselves."""
+        if getattr(self.refiner, "mlp", "torch") == "tcgen05":
+            ops.refiner_range_check()
+
     @torch.no_grad()
     def run_pairs(self, saliency, features, pair_index, variant=matchers.M1, chunk=256, timers=None, **kw):
         """Extract every frame once (in chunks) into a resident bank and match the listed (a, b)
@@ -197,6 +205,7 @@ class FrontEnd:
         for dst, src in zip(out_host, res):
             dst.copy_(src, non_blocking=True)
         compute.synchronize()
+        self.check_range()
         return out_host
 
     def _staging(self, saliency_host, features_host, chunk, dev):
@@ -293,4 +302,5 @@ class FrontEnd:
                 for dst, src in zip(out_host, res):
                     dst[p0:e - 1].copy_(src, non_blocking=True)
         compute.synchronize()
+        self.check_range()
         return out_host

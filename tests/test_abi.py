@@ -50,7 +50,7 @@ def test_header_symbols_exported(lib):
 
 def test_abi_version_and_workspace_queries(lib):
     l = lib.load()
-    assert l.sslam_abi_version() == 3
+    assert l.sslam_abi_version() == 4
     assert l.sslam_decode_workspace_bytes(2, 480, 640, 2048) >= 2 * 480 * 640 * 8
     assert l.sslam_match_workspace_bytes(3, 3, 3, 2048, 2048, 256, 0) >= 3 * 2048 * 8
     assert l.sslam_decode_workspace_bytes(0, 480, 640, 1) == 0

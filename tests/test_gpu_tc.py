@@ -405,3 +405,88 @@ def test_c5_hires_pair(dev):
                           pairs[0, :int(counts[0])].cpu().numpy())
     assert int(counts[0]) > K // 4
     record("c5_hires_pair", {"matches": int(counts[0]), "near_tie_exceptions": int(exc)})
+
+
+def _refiner_fp64(m, x):
+    """DescriptorRefiner forward in float64 (models/descriptor_refiner.py:73-86, 108-126) from the module's own weights."""
+    sd = {k: v.detach().cpu().double() for k, v in m.state_dict().items()}
+    h = torch.relu(x.cpu().double().reshape(-1, x.shape[-1]) @ sd["input_proj.weight"].T + sd["input_proj.bias"])
+    i = 0
+    while f"residual_blocks.{i}.fc1.weight" in sd:
+        pre = f"residual_blocks.{i}."
+        def ln(t, w, b):
+            mu = t.mean(-1, keepdim=True)
+            var = ((t - mu) ** 2).mean(-1, keepdim=True)
+            return (t - mu) / torch.sqrt(var + 1e-5) * w + b
+        u = torch.relu(ln(h, sd[pre + "norm1.weight"], sd[pre + "norm1.bias"]) @ sd[pre + "fc1.weight"].T + sd[pre + "fc1.bias"])
+        u = ln(u, sd[pre + "norm2.weight"], sd[pre + "norm2.bias"]) @ sd[pre + "fc2.weight"].T + sd[pre + "fc2.bias"]
+        h = torch.relu(u + h)
+        i += 1
+    d = h @ sd["output_proj.weight"].T + sd["output_proj.bias"]
+    return d / d.norm(dim=-1, keepdim=True).clamp_min(1e-12)
+
+
+def test_refiner_trained_like_weights_and_range_guard(dev):
+    """Weights and inputs unlike a fresh initialisation: LayerNorm gains 0.3..2.5 and shifts
+    +-1, biases that put the row mean several standard deviations from zero (the one-pass variance
+    E[x^2]-mu^2 of the folded LayerNorm cancels there), scaled weights, inputs with an offset and with
+    outlier channels of magnitude ~400 as DINO features have.  Descriptors stay within 1e-5 of a float64
+    evaluation.  And the range guard: inputs that push an activation past the fp16 range make forward()
+    raise SSLAM_ERANGE instead of returning NaN, after which the flag is clear again."""
+    from models.descriptor_refiner import DescriptorRefiner
+    from sslam_b200 import ops, _lib
+    torch.manual_seed(7)
+    m = DescriptorRefiner(384, 384, 256, 4).to(dev).eval()
+    with torch.no_grad():
+        m.input_proj.weight.mul_(1.7)
+        m.input_proj.bias.add_(2.0)
+        for blk in m.residual_blocks:
+            for lnm in (blk.norm1, blk.norm2):
+                lnm.weight.uniform_(0.3, 2.5)
+                lnm.bias.uniform_(-1.0, 1.0)
+            blk.fc1.weight.mul_(1.5); blk.fc1.bias.add_(1.0)
+            blk.fc2.weight.mul_(0.7); blk.fc2.bias.add_(3.0)
+        m.output_proj.weight.mul_(2.0)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 3000, 384, generator=g) * 4.0 + 1.5
+    x[..., 7] *= 50.0                                       # outlier channels
+    x[..., 200] = x[..., 200] * 30.0 + 100.0
+    x = x.to(dev)
+    with torch.no_grad():
+        out = m(x)[0].double().cpu()
+    ref = _refiner_fp64(m, x)
+    err = float((out - ref).abs().max())
+    # row statistics of the LayerNorm inputs, for the record: how far the mean is from zero in units of std
+    with torch.no_grad():
+        h = torch.relu(m.input_proj(x[0]))
+    ratio = float((h.mean(-1).abs() / h.std(-1)).max())
+    record("refiner_trained_like", {"max_abs_err_vs_fp64": err, "max_row_mean_over_std": ratio})
+    print(f"trained-like refiner: max|gpu - fp64| = {err:.2e}, max |row mean| / std of the first LayerNorm input = {ratio:.1f}")
+    assert err < 1e-5
+    ops.refiner_range_check()                               # nothing left the range
+    # rows whose mean is tens of standard deviations from zero (bias shift 40 on every LayerNorm input)
+    m2 = DescriptorRefiner(384, 384, 256, 4).to(dev).eval()
+    with torch.no_grad():
+        m2.input_proj.bias.add_(40.0)
+        for blk in m2.residual_blocks:
+            blk.fc2.bias.add_(40.0)
+    xs = torch.randn(1, 2000, 384, generator=torch.Generator().manual_seed(3)).to(dev)
+    with torch.no_grad():
+        o2 = m2(xs)[0].double().cpu()
+        h2 = torch.relu(m2.input_proj(xs[0]))
+    err2 = float((o2 - _refiner_fp64(m2, xs)).abs().max())
+    ratio2 = float((h2.mean(-1).abs() / h2.std(-1)).max())
+    record("refiner_shifted_rows", {"max_abs_err_vs_fp64": err2, "max_row_mean_over_std": ratio2})
+    print(f"shifted rows: max|gpu - fp64| = {err2:.2e} at |row mean| / std up to {ratio2:.0f}")
+    assert err2 < 1e-5 and ratio2 > 30
+    # out of range: hidden activations ~ 1e5
+    with torch.no_grad():
+        try:
+            m(x * 3.0e3)
+            raised = False
+        except _lib.SslamError as e:
+            raised = e.code == -6
+    assert raised, "forward() must raise SSLAM_ERANGE when an activation leaves the fp16 range"
+    with torch.no_grad():
+        out2 = m(x)[0].double().cpu()                       # flag cleared, results unchanged
+    assert torch.equal(out2, out)
