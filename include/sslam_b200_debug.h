@@ -25,6 +25,9 @@ int sslam_debug_watchdog_gemm(unsigned long long* buf);
  * streaming scan does not take); non-zero (default): streaming scan + histogram top-k where eligible. */
 void sslam_debug_decode_stream(int on);
 
+/* Streaming decode scan: stages of the shared-memory ring per CTA and rows per band (0 = library default). */
+void sslam_debug_decode_tune(int stages, int band_rows);
+
 /* DescriptorRefiner forward: 0 = one GEMM launch per layer; 1..4 = the layer-fused persistent kernel with
  * that many 256-row strip pairs per chunk (default 3).  Both paths compute bit-identical results. */
 void sslam_debug_refiner_fused(int mode);

@@ -33,6 +33,7 @@
 
 namespace sslam {
 bool g_decode_no_stream = false;         // tools / tests: force the register-prefetching scan kernels
+int g_decode_ns = 0, g_decode_band = 0;  // tools: stages per CTA / rows per band of the streaming scan (0 = default)
 namespace {
 
 constexpr int TILE_W = 128;
@@ -375,8 +376,8 @@ __device__ __forceinline__ void bar_wait(u32 bar, u32 parity) {
 
 constexpr int STREAM_MAX_WARPS = 15;     // consumer warps = strips of 120 columns
 
-template <int R>
-__global__ void __launch_bounds__(32 * (STREAM_MAX_WARPS + 1))
+template <int R, bool LOGITS>
+__global__ void __launch_bounds__(32 * (STREAM_MAX_WARPS + 1), R <= 2 ? 2 : 1)   // R <= 2: <= 64 registers, four 224-thread CTAs per SM at W = 640
 decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows, int NS) {
   constexpr int WIN = 2 * R + 1, OUTW = 120, CAP = 2048;
   extern __shared__ __align__(128) unsigned char dsm[];
@@ -409,9 +410,9 @@ decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows
     // ---- producer: stage s holds rows first + s*WIN .. +WIN-1; rows outside the image are not
     // loaded (the consumers mask them by index)
     if (lane == 0) {
+      int slot = 0; u32 lap = 0;                              // s = lap * NS + slot
       for (int s = 0; s < nstage; ++s) {
-        const int slot = s % NS;
-        if (s >= NS) bar_wait(empty0 + 8 * slot, ((s / NS) - 1) & 1);
+        if (lap) bar_wait(empty0 + 8 * slot, (lap - 1) & 1);
         const int r0 = first + s * WIN;
         const int a = max(r0, 0), e = min(min(r0 + WIN, H), y_end);
         const u32 bytes = e > a ? (u32)(e - a) * (u32)W * 4u : 0u;
@@ -424,6 +425,7 @@ decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows
         } else {
           asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
         }
+        if (++slot == NS) { slot = 0; ++lap; }
       }
     }
   } else if (warp < nstrips) {
@@ -444,9 +446,9 @@ decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows
 #pragma unroll
       for (int c = 0; c < 4; ++c) { hwin[i][c] = NEG_INF; cwin[i][c] = NEG_INF; }
 
+    int slot = 0; u32 lap = 0;
     for (int s = 0; s < nstage; ++s) {
-      const int slot = s % NS;
-      bar_wait(full0 + 8 * slot, (s / NS) & 1);
+      bar_wait(full0 + 8 * slot, lap & 1);
       const unsigned char* st = dsm + slot * stage_bytes;
       const int yy = first + s * WIN;
 #pragma unroll
@@ -456,7 +458,7 @@ decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows
           float4 v4 = make_float4(NEG_INF, NEG_INF, NEG_INF, NEG_INF);
           if (col_ok && yc >= 0 && yc < H) {
             v4 = *reinterpret_cast<const float4*>(st + ((size_t)u * W + x) * 4);
-            if (p.from_logits) { v4.x = sigmoid_f32(v4.x); v4.y = sigmoid_f32(v4.y); v4.z = sigmoid_f32(v4.z); v4.w = sigmoid_f32(v4.w); }
+            if (LOGITS) { v4.x = sigmoid_f32(v4.x); v4.y = sigmoid_f32(v4.y); v4.z = sigmoid_f32(v4.z); v4.w = sigmoid_f32(v4.w); }
           }
           float e[4 + 2 * R];
           const float own[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -505,6 +507,7 @@ decode_scan_stream_kernel(DecodeParams p, int nstrips, int nbands, int band_rows
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty0 + 8 * slot) : "memory");
+      if (++slot == NS) { slot = 0; ++lap; }
     }
     below = warp_reduce_sum(below);
     if (lane == 0 && below) atomicAdd(&hdr->spec_below, below);
@@ -975,23 +978,33 @@ extern "C" int sslam_decode_topk_f32(const float* sal, int from_logits, int B, i
   bool hist_topk = false;
   if (stream_ok) {
     SSLAM_CHECK_CUDA(cudaMemsetAsync(p.chist, 0, (size_t)B * HIST_BINS * sizeof(u32), stream));
-    int NS = (int)((88 * 1024) / stream_stage);
+    // Residency beats ring depth (c2, 300 maps per launch): 7 stages x 2 CTAs per SM 0.26 ms, 4 x 3 CTAs 0.19,
+    // 2 x 4 CTAs 0.177 — the scan is bound by instruction issue and latency, not by bytes in flight, so
+    // the ring is kept at about 26 KB (two stages at W = 640) and the bands at 64 rows (a band's ~1500
+    // local maxima then fit the 2048-key staging list: no overflow appends to the global list)
+    int NS = (int)((26 * 1024) / stream_stage);
+    if (NS < 2) NS = 2;
     if (NS > 16) NS = 16;
-    const int nbands = (H + 127) / 128;
+    if (g_decode_ns > 0) NS = g_decode_ns < 2 ? 2 : (g_decode_ns > 16 ? 16 : g_decode_ns);
+    if ((size_t)NS * stream_stage > 88 * 1024) NS = (int)((88 * 1024) / stream_stage);
+    const int band_target = g_decode_band > 0 ? g_decode_band : 64;
+    const int nbands = (H + band_target - 1) / band_target;
     const int band_rows = (H + nbands - 1) / nbands;
     const size_t dyn = (size_t)NS * stream_stage;
     static DeviceOnce once_stream;
     if (once_stream.first_use()) {
-      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
-      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
-      SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024));
+#define SSLAM_SCAN_ATTR(R_, L_) SSLAM_CHECK_CUDA(cudaFuncSetAttribute(decode_scan_stream_kernel<R_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 88 * 1024))
+      SSLAM_SCAN_ATTR(1, false); SSLAM_SCAN_ATTR(2, false); SSLAM_SCAN_ATTR(3, false);
+      SSLAM_SCAN_ATTR(1, true); SSLAM_SCAN_ATTR(2, true); SSLAM_SCAN_ATTR(3, true);
+#undef SSLAM_SCAN_ATTR
     }
     const unsigned blocks = (unsigned)(B * nbands);
     const unsigned threads = 32u * (unsigned)(stream_strips + 1);
+#define SSLAM_SCAN_GO(R_, L_) decode_scan_stream_kernel<R_, L_><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS)
     SSLAM_LAUNCH(KK_DECODE_SCAN, stream,
-                 if (r == 1) decode_scan_stream_kernel<1><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS);
-                 else if (r == 2) decode_scan_stream_kernel<2><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS);
-                 else decode_scan_stream_kernel<3><<<blocks, threads, dyn, stream>>>(p, stream_strips, nbands, band_rows, NS));
+                 if (from_logits) { if (r == 1) SSLAM_SCAN_GO(1, true); else if (r == 2) SSLAM_SCAN_GO(2, true); else SSLAM_SCAN_GO(3, true); }
+                 else { if (r == 1) SSLAM_SCAN_GO(1, false); else if (r == 2) SSLAM_SCAN_GO(2, false); else SSLAM_SCAN_GO(3, false); });
+#undef SSLAM_SCAN_GO
     hist_topk = true;
   } else if (r >= 1 && r <= 3 && vec_ok) {
     const int nstrips = (W + 119) / 120;                       // 120 output columns per warp
@@ -1078,3 +1091,4 @@ extern "C" int sslam_nms_f32(const float* sal, int B, int H, int W, int nms_radi
 // Debug aid for tests / tools (include/sslam_b200_debug.h): 0 forces the register-prefetching scan
 // kernels + radix-select top-k instead of the shared-memory streaming scan + histogram top-k.
 extern "C" void sslam_debug_decode_stream(int on) { sslam::g_decode_no_stream = (on == 0); }
+extern "C" void sslam_debug_decode_tune(int stages, int band_rows) { sslam::g_decode_ns = stages; sslam::g_decode_band = band_rows; }

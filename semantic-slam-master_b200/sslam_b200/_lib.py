@@ -65,6 +65,7 @@ DEBUG_SIGNATURES = {
     "sslam_debug_watchdog_gemm": (c_int, [c_void_p]),
     "sslam_debug_decode_stream": (None, [c_int]),
     "sslam_debug_refiner_fused": (None, [c_int]),
+    "sslam_debug_decode_tune": (None, [c_int, c_int]),
 }
 
 ERROR_NAMES = {-1: "SSLAM_EINVAL", -2: "SSLAM_EUNSUPPORTED", -3: "SSLAM_EWORKSPACE",
