@@ -718,7 +718,7 @@ def run_b200(a):
                   "this fraction is 1/3 = 0.333 (1/6 for the tf32x3 variant)")
     if work.get(dom, ("", 0))[0] == "tensor":
         ach = dk["algorithmic_TFLOP/s"]
-        traffic = ncu_traffic(dom, rows / max(dk["launches_per_step"] / 6.0, 1e-9)) if dom == "gemm_f16x3" else None
+        traffic = ncu_traffic(dom, rows / max(dk["launches_per_step"], 1e-9)) if dom == "gemm_f16x3" else None
         roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                     "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src + ", bf16 dense sustained",

@@ -60,5 +60,35 @@ def raw(path):
                 print(f"  {m:75s} {row[i]:>18s} {units[i]}")
 
 
+def traffic(path, kernel_substr, bench_key, rows_per_launch, out_json):
+    """dram bytes (read + write) per launch of the kernels whose name contains `kernel_substr`, averaged over
+    the report's launches of it, recorded per input row under `bench_key` in `out_json`
+    (profiles/ncu_traffic.json: bench.py's roofline.traffic reads it and scales it to the run's rows per launch).
+        python profiles/summarize_ncu.py traffic gpurun_out/prof.ncu-rep refiner_fused gemm_f16x3 614400 profiles/ncu_traffic.json"""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    for row in rows[2:]:
+        if kernel_substr in row[ik]:
+            tot += float(row[ir].replace(",", "")) * scale[units[ir]] + float(row[iw].replace(",", "")) * scale[units[iw]]
+            n += 1
+    rec = {}
+    if os.path.exists(out_json):
+        rec = json.load(open(out_json))
+    rec[bench_key] = {"dram_bytes_per_row": tot / n / float(rows_per_launch), "dram_bytes_per_launch": tot / n,
+                      "rows_per_launch": int(rows_per_launch), "launches_averaged": n, "kernel": kernel_substr,
+                      "capture": os.path.basename(path)}
+    json.dump(rec, open(out_json, "w"), indent=1)
+    print(json.dumps(rec[bench_key]))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:7])
+    else:
+        {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
