@@ -363,7 +363,10 @@ gemm_f16x3_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
 // tcgen05.commit multicasts `empty` / `tfull` to both CTAs; both epilogues arrive on the leader's
 // `tempty`.
 constexpr int P_STAGES = 3;
-constexpr int P_MAX_KB = 6;                               // K <= 384
+#ifndef SSLAM_P_MAX_KB
+#define SSLAM_P_MAX_KB 6
+#endif
+constexpr int P_MAX_KB = SSLAM_P_MAX_KB;                  // K <= 384
 constexpr int B_HALF = 64 * 128;                          // 64 weight rows x 128 bytes of K
 constexpr int P_STAGE_BYTES = 2 * BLOCK_BYTES;            // A_hi, A_lo
 constexpr int P_SMEM_B = P_MAX_KB * 2 * B_HALF;
@@ -771,7 +774,11 @@ constexpr int F_STAGE_BYTES = 2 * F_HALF_BYTES;           // A_hi, A_lo
 // (7 stages of 32 columns, 8 KB per request: 3.4 ms instead of 2.9 — the cost of a multicast request is about
 // 160 cycles + 1 cycle per 73 bytes, so the feed wants few, large requests)
 static_assert(F_BK == 64, "the stage of the fused kernel is one 64-column block");
-constexpr int F_STAGES = 3;
+// (a fourth 32 KB stage, tried at K = 320 where it fits: 2.60 instead of 2.62 ms — the ring depth is not the limit)
+#ifndef SSLAM_F_STAGES
+#define SSLAM_F_STAGES 3
+#endif
+constexpr int F_STAGES = SSLAM_F_STAGES;
 constexpr int F_SUB = BK / F_BK;                          // stages per 64-element weight k-block
 constexpr int F_SMEM_A = F_STAGES * F_STAGE_BYTES;
 constexpr int F_SMEM_VECS = F_MAX_LAYERS * 2 * BN * 4;    // [layer][bias 128 | s1 128] of the pair's columns

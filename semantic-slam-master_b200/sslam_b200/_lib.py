@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsslam_b200.so")
+LIB_PATH = os.environ.get("SSLAM_B200_LIB") or os.path.join(_HERE, "libsslam_b200.so")   # (override: tools / experiments)
 
 c_int, c_float, c_size_t, c_void_p = ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_void_p
 

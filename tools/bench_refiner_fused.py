@@ -10,8 +10,9 @@ from sslam_b200 import ops, _lib
 F = int(os.environ.get("F", 300))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-m = DescriptorRefiner(384, 384, 256, 4).to(dev).eval()
-x = torch.randn(1, F * 2048, 384, device=dev)
+CIN, HD = int(os.environ.get('CIN', 384)), int(os.environ.get('HD', 384))
+m = DescriptorRefiner(CIN, HD, 256, 4).to(dev).eval()
+x = torch.randn(1, F * 2048, CIN, device=dev)
 lib = _lib.load()
 MODES = [int(v) for v in os.environ.get("MODES", "0,1,2,3,4").split(",")]
 REPS = int(os.environ.get("REPS", 5))
