@@ -698,7 +698,9 @@ def run_b200(a):
         "match_tc": ("tensor", mm_flops), "match_f32": ("tensor", mm_flops),
         "decode_scan": ("hbm", (4.0 * a.H * a.W + 12 * K) * Tl),
         "gather": ("hbm", (4.0 * (a.H // 16) * (a.W // 16) * C + 8 * K + 4 * K * C) * Tl),
-        "l2norm": ("hbm", 8.0 * K * D * Tl),
+        # fp32 in, fp32 out, plus the operand copy the matcher reads (fp16 hi/lo pair: 4 B, bf16: 2 B) — written
+        # here instead of by a split pass in front of the matcher
+        "l2norm": ("hbm", (8.0 + {"f16x3": 4.0, "bf16": 2.0}.get(a.mode_name, 0.0)) * K * D * Tl),
     }
     kernels = {}
     for kind, (ms_tot, n) in kernel_ms.items():
