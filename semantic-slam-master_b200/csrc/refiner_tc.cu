@@ -1300,7 +1300,7 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
           if (l + 1 < L) {                                        // P(l, s)
             if (lane == 0) {
               mbar_wait(&tdone[tcn & 3u], (tcn >> 2) & 1u);
-              asm volatile("fence.release.cluster;" ::: "memory");
+              if (!(p.dbg_flags & 8192)) asm volatile("fence.release.cluster;" ::: "memory");   // (debug 8192: timing without the fence)
               const uint32_t rb = smem_u32(&ready[s]);
               for (uint32_t j = 0; j < ncta; ++j) mbar_arrive_cluster_relaxed(mapa_u32(rb, j));
             }
