@@ -26,12 +26,13 @@
 //     and its epilogue applies the two per-row scalars; those (mu_r, rho_r) are produced for free by
 //     the epilogue of the GEMM that wrote h (row sums of v and v^2 while storing).
 //
-// Two kernels.  gemm_pair_kernel (further down) is the production path for K <= 384, N <= 512:
-// weight-stationary CTA pairs (cta_group::2, M = 256), the pairs of the column tiles of one strip
-// set forming a cluster that multicasts the activation tiles.  gemm_f16x3_kernel (directly below)
-// is the general single-CTA fallback: persistent, one CTA per SM, each CTA walks 128-row strips
-// (blockIdx, +gridDim, ...) and, inside a strip, the N/128 column tiles of the layer, streaming
-// both operands.
+// Three kernels.  refiner_fused_kernel (last in this file) is the production path for C, Hd <= 384:
+// ONE persistent launch for all layers, weight-stationary CTA pairs (cta_group::2, M = 256) in clusters
+// that multicast the activation blocks, activations exchanged between layers through an L2-resident
+// scratch in the UMMA operand layout.  gemm_pair_kernel is the same data path with one launch per layer
+// (fallback, and the bit-exact cross-check of the fused kernel); gemm_f16x3_kernel (directly below) is
+// the general single-CTA fallback: persistent, one CTA per SM, each CTA walks 128-row strips and,
+// inside a strip, the N/128 column tiles of the layer, streaming both operands.
 #include "tc_common.cuh"
 
 namespace sslam {
@@ -728,7 +729,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 //   * same cluster shape and data path as gemm_pair_kernel: `ntile` CTA pairs (cta_group::2, M = 256),
 //     pair ct owns output columns [128 ct, 128 ct + 128) of EVERY layer; activation k-blocks are TMA-
 //     multicast to the pairs; the epilogue threads store their rows of the fp16 pair straight from
-//     registers (32-byte sectors).
+//     registers into the scratch, whose layout is the core-matrix operand layout (see SCR_CHUNK below).
 //   * a cluster works on chunks of S strip pairs (S x 256 rows).  Order inside a chunk: layer-major,
 //     strip-minor (l0: s0..sS-1, l1: s0..sS-1, ...).  The layer outputs go to a per-cluster scratch
 //     (h and u pairs, S x 256 rows each: groups x S x 768 KB = ~50 MB for 22 clusters and S = 3) that
@@ -736,10 +737,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_consta
 //     once, nothing but the final descriptors is written back to DRAM.  fc2 + identity updates h in
 //     place (the thread that adds the residual element is the one that stores it).
 //   * strip s of layer l+1 may be loaded once all 2*ntile CTAs have stored their columns of strip s of
-//     layer l: each epilogue warp, half a tile after its last store, issues a release fence and
-//     arrives on the `ready[s]` mbarrier of every CTA of the cluster; the producers wait on it, acquire
-//     and order their TMA loads behind it (fence.proxy.async).  With S >= 3 the wait has more than a
-//     tile of slack and never stalls the tensor pipe.
+//     layer l: a publisher warp waits for the CTA's eight epilogue warps, issues ONE release fence at
+//     cluster scope and arrives on the `ready[s]` mbarrier of every CTA of the cluster; the producers
+//     wait on it and order their TMA loads behind it (fence.proxy.async).  With S >= 3 the wait has
+//     more than a tile of slack and never stalls the tensor pipe.
 //   * weights are layer-stationary instead of launch-stationary: a dedicated warp reloads the pair's
 //     128 weight columns k-block by k-block behind the last strip of the previous layer (`wfree[kb]`
 //     is committed by that strip's MMAs, `wfull[kb]` gates the first strip of the next layer), so the
@@ -753,11 +754,8 @@ constexpr int F_MAX_SLOTS = 4;                            // strip pairs per chu
 constexpr int F_THREADS = NUM_THREADS + 64;               // + the weight producer warp and the publisher warp
 constexpr int F_W_WARP = NUM_THREADS / 32;
 constexpr int F_PUB_WARP = F_W_WARP + 1;
-// Activation stages: F_BK K-elements of the CTA's 128 rows, hi and lo.  Measured on c2 (300 frames, S = 3):
-//   3 x 32 KB (F_BK 64, SWIZZLE_128B)  3.4 - 3.6 ms      7 x 16 KB (F_BK 32, SWIZZLE_64B)  3.9 - 4.1 ms
-//   4 x 32 KB (all of shared memory, bias vectors read through L1 instead)  5.0 ms
-// i.e. the feed is not short of bytes in flight: both the per-layer kernel and this one settle at about
-// 192 KB of A operand per 8.5 - 9k cycles and SM (~22 B/clk).
+// Activation stages: F_BK K-elements of the CTA's 128 rows, hi and lo (32 KB).  What bounds the kernel is
+// measured in DESIGN.md 4.5 (tools/fused_probe.py): neither the ring depth nor the request size.
 constexpr int F_BK = 64;
 // Scratch activations (h, u): per 128-row strip and 64-column block one 32 KB piece = exactly one stage of
 // the A operand, [hi | lo][column / 8 (8 chunks)][row / 8][row % 8][column % 8] — the no-swizzle core-matrix
