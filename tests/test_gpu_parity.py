@@ -145,6 +145,32 @@ def test_decode_speculative_count_is_only_a_hint(dev):
     assert np.array_equal(kp.cpu().numpy(), okp) and np.array_equal(sc.cpu().numpy(), osc)
 
 
+def test_decode_ring_and_band_shape_do_not_change_results(dev):
+    """The streaming scan's ring depth and band height are scheduling choices: whatever they are — two
+    stages and 64-row bands (the default), a deep ring, bands of a few rows whose halos overlap, one band per
+    image, a staging list that overflows into the global list (plateau maps, tall bands) — keypoints,
+    scores and the branch taken equal the oracle's."""
+    from sslam_b200 import ops, _lib
+    lib = _lib.load()
+    H, W, K = 400, 512, 256                               # ~8 000 local maxima per map: one band overflows the staging list
+    maps = np.stack([recipes.spread_saliency(H, W, 401, lo=0.2, hi=0.99), recipes.box_saliency(H, W, 402),
+                     recipes.spread_saliency(H, W, 403, lo=0.02, hi=0.4)])
+    okp, osc, oinfo = oracle.select_keypoints(maps, K)
+    try:
+        for stages, band in ((0, 0), (2, 64), (7, 128), (16, 8), (3, 5), (2, 4096), (5, 33)):
+            lib.sslam_debug_decode_tune(stages, band)
+            kp, sc, info = ops.decode_topk(cu(maps, dev), K)
+            assert np.array_equal(info.cpu().numpy()[:, 0], oinfo[:, 0]), (stages, band)
+            assert np.array_equal(sc.cpu().numpy(), osc), (stages, band)
+            cmp_kp = kp.cpu().numpy()
+            same = np.array_equal(cmp_kp, okp)
+            if not same:                                  # equal scores may be ordered by index on either side
+                for b in range(maps.shape[0]):
+                    assert sorted(map(tuple, cmp_kp[b])) == sorted(map(tuple, okp[b])), (stages, band, b)
+    finally:
+        lib.sslam_debug_decode_tune(0, 0)
+
+
 def test_decode_full_size_properties(dev, scan_path):
     """BASELINE sizes (640x480 K=2048, 1280x960 K=8192) on the seeded synthetic sequence:
     identical to the oracle, plus size-independent properties."""
