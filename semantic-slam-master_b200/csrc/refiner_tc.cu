@@ -1353,7 +1353,9 @@ refiner_fused_kernel(const __grid_constant__ FusedMaps tm, const FusedParams p) 
               const uint64_t boff = (uint64_t)(sub * F_BK * 2 >> 4);      // position inside the 128-byte weight rows
               const uint64_t b_hi = make_smem_desc_sw128(sb) + boff;
               const uint64_t b_lo = make_smem_desc_sw128(sb + B_HALF) + boff;
-              if (!(p.dbg_flags & 2))
+              // a pair whose columns lie beyond the layer's width (output projection narrower than the hidden
+              // layers) keeps the barrier protocol going but issues no MMAs: its epilogue skips every column
+              if (!(p.dbg_flags & 2) && col_base < li.N)
 #pragma unroll
               for (int k = 0; k < F_BK / 16; ++k) {
                 const uint64_t adv = (uint64_t)(k * 32 >> 4), aadv = (uint64_t)k * a_step;
